@@ -1,0 +1,154 @@
+/*
+ * pyvr_cuda.h -- C ABI of the B200-native (sm_100a) backend for PyVR's volume ray-march path.
+ *
+ * The reference (JixianLi/pyvr v0.4.1) has no FFI: its renderer is a Python class that drives an
+ * OpenGL context through moderngl.  The boundary this library replaces is therefore the
+ * ModernGLManager resource layer (pyvr/moderngl_renderer/manager.py) plus the fragment shader
+ * (pyvr/shaders/volume.frag.glsl); each entry point below names the manager method / uniform /
+ * shader stage it stands in for.  The Python side (pyvr_b200/cuda_renderer) binds these with
+ * ctypes; INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions: every function returns 0 on success and a negative pyvr_status on failure;
+ * pyvr_cuda_last_error() returns a thread-local description of the last failure.  All pointers
+ * are plain host pointers unless a *_is_device argument says otherwise.  A context is bound to
+ * one CUDA device and must not be used from two threads at once (the reference's GL context
+ * is thread-affine in the same way).
+ */
+#ifndef PYVR_CUDA_H
+#define PYVR_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PYVR_CUDA_ABI_VERSION 1
+
+typedef enum {
+    PYVR_OK = 0,
+    PYVR_ERR_INVALID = -1,   /* bad argument */
+    PYVR_ERR_CUDA = -2,      /* a CUDA runtime call failed */
+    PYVR_ERR_STATE = -3,     /* e.g. render before a volume / LUT was uploaded is fine, but
+                                a batch render without a volume is not */
+    PYVR_ERR_NOMEM = -4
+} pyvr_status;
+
+/* Texel storage of the packed scalar+normal volume. */
+typedef enum {
+    PYVR_TEXEL_F32X4 = 0,    /* {scalar, nx, ny, nz} binary32, 16 B / voxel (parity configs) */
+    PYVR_TEXEL_F16X4 = 1     /* same in binary16, 8 B / voxel (2048^3 / 4096^3 configs) */
+} pyvr_texel_format;
+
+/* pyvr_params.flags */
+#define PYVR_FLAG_STRICT   0x1u  /* reference-faithful arithmetic: incremental position, IEEE div/sqrt/exp,
+                                    no empty-space skipping (used to compare against the oracle bit for bit) */
+#define PYVR_FLAG_ESS      0x2u  /* macrocell empty-space skipping (exact: skips only zero contributions) */
+#define PYVR_FLAG_NO_BLEND 0x4u  /* RGBA8 output holds (C, A) instead of the reference's blended (C*A, A*A) */
+
+typedef struct pyvr_ctx pyvr_ctx;
+
+/*
+ * Ray basis of one view: for pixel centre (px+0.5, py+0.5), ndc = 2*(p/size) - 1 and
+ *   dir = normalize(u * ndc.x + v * ndc.y + w),  origin = camera position.
+ * This is the closed form of ray_direction() (volume.frag.glsl:47-54) for ANY view/projection
+ * matrices: inverse(P) and inverse(V) are applied once on the host instead of per fragment.
+ * py = 0 is the BOTTOM row, as in the GL framebuffer the reference reads back.
+ */
+typedef struct {
+    float origin[3];
+    float u[3];
+    float v[3];
+    float w[3];
+} pyvr_view;
+
+/* Uniforms of the shader other than camera and bounds (volume.frag.glsl:10-19). */
+typedef struct {
+    float step_size;            /* uniform step_size            (renderer.py:305) */
+    int32_t max_steps;          /* uniform max_steps            (renderer.py:306) */
+    float reference_step_size;  /* uniform reference_step_size  (renderer.py:307-309) */
+    float ambient;              /* uniform ambient_light        (renderer.py:313) */
+    float diffuse;              /* uniform diffuse_light        (renderer.py:314) */
+    float light_position[3];    /* uniform light_position       (renderer.py:315) */
+    float light_target[3];      /* uniform light_target         (renderer.py:316) */
+    float termination_alpha;    /* the shader hard-codes 0.99 (volume.frag.glsl:87); pass 0.99 for parity */
+    uint32_t flags;             /* PYVR_FLAG_* */
+} pyvr_params;
+
+typedef struct {
+    uint64_t samples;           /* in-box loop bodies of volume.frag.glsl:92-116 the reference would execute */
+    uint64_t samples_fetched;   /* of those, how many actually fetched texels (== samples without ESS) */
+    uint64_t rays_hit;          /* rays that pass intersect_box */
+    uint64_t rays_terminated;   /* rays stopped by the accumulated-alpha test */
+    float kernel_ms;            /* device time of the march kernel(s) of the last render call (CUDA events) */
+    uint32_t kernel_launches;   /* kernels launched by the last render call */
+    uint32_t views;             /* views rendered by the last render call */
+} pyvr_stats;
+
+/* --- life cycle: ModernGLManager.__init__ / cleanup (manager.py:14-41, 238-256) ------------------ */
+int pyvr_cuda_create(int device, int width, int height, pyvr_ctx **out_ctx);
+int pyvr_cuda_destroy(pyvr_ctx *ctx);
+/* Run all work of this context on an existing cudaStream_t (0 = the context's own stream). */
+int pyvr_cuda_set_stream(pyvr_ctx *ctx, void *cuda_stream);
+
+/* --- create_volume_texture + create_normal_texture + bounds uniforms
+ *     (manager.py:77-135, renderer.py:131-146) ----------------------------------------------------
+ * scalar: shape0*shape1*shape2 floats in numpy C order.  normals: the same voxels x 3 floats, or
+ * NULL (the shader then sees normal = (density, 0, 0)).
+ * The reference hands `shape` to moderngl as (width, height, depth) over the C-order bytes; the
+ * library reproduces that addressing exactly (identical to data[ix,iy,iz] for cubic volumes).
+ * src_is_device != 0: both pointers are device pointers on this context's device. */
+int pyvr_cuda_upload_volume(pyvr_ctx *ctx, const float *scalar, const float *normals,
+                            int shape0, int shape1, int shape2,
+                            const float bmin[3], const float bmax[3],
+                            int texel_format, int src_is_device);
+
+/* --- create_rgba_transfer_function_texture (manager.py:137-186): (size,4) RGBA binary32 ---------- */
+int pyvr_cuda_set_lut(pyvr_ctx *ctx, const float *rgba, int size);
+
+/* --- set_camera (renderer.py:148-172): the three uniforms as the reference writes them:
+ *     16 floats of view_matrix.tobytes(), 16 of projection_matrix.tobytes() (GL reads both
+ *     column-major) and camera_pos.  Derives the pyvr_view on the host in binary64. ---------------- */
+int pyvr_cuda_set_camera(pyvr_ctx *ctx, const float view[16], const float proj[16], const float cam_pos[3]);
+/* Same derivation without a context (used to build batches). */
+int pyvr_cuda_view_from_matrices(const float view[16], const float proj[16], const float cam_pos[3],
+                                 pyvr_view *out);
+int pyvr_cuda_set_view(pyvr_ctx *ctx, const pyvr_view *view);
+
+/* --- _update_render_config + _update_light (renderer.py:303-316) --------------------------------- */
+int pyvr_cuda_set_params(pyvr_ctx *ctx, const pyvr_params *params);
+
+/* --- render(): clear + blend + draw + fbo.read (renderer.py:209-219, manager.py:212-230) ---------
+ * out: width*height*4 bytes RGBA8, row 0 = bottom.  out_is_device != 0: device pointer.
+ * Rendering with no volume or no LUT loaded yields the cleared frame (all zero), as the reference
+ * tolerates (tests/test_moderngl_renderer/test_volume_renderer.py:306-327). */
+int pyvr_cuda_render(pyvr_ctx *ctx, uint8_t *out, int out_is_device);
+/* n views in one call; out holds n consecutive frames. */
+int pyvr_cuda_render_batch(pyvr_ctx *ctx, const pyvr_view *views, int n, uint8_t *out, int out_is_device);
+/* The fragment colour BEFORE blending/quantisation, width*height*4 floats (acc_rgb, acc_a). */
+int pyvr_cuda_render_accum(pyvr_ctx *ctx, float *out, int out_is_device);
+
+int pyvr_cuda_get_stats(pyvr_ctx *ctx, pyvr_stats *out);
+
+/* --- compute_normal_volume (pyvr/datasets/synthetic.py:109-122) ----------------------------------
+ * in: n0*n1*n2 floats (C order); out: n0*n1*n2*3 floats.  buffers_are_device != 0: both are device
+ * pointers on `device`.  kernel_ms (may be NULL) receives the stencil kernel's device time. */
+int pyvr_cuda_compute_normals(int device, const float *in, float *out, int n0, int n1, int n2,
+                              int buffers_are_device, float *kernel_ms);
+
+/* --- misc ------------------------------------------------------------------------------------------ */
+/* Tuning knobs (no reference counterpart).  "layout": 0 = linear texel array, 1 = 8^3 bricks (default);
+ * must be set before pyvr_cuda_upload_volume. */
+int pyvr_cuda_set_option(pyvr_ctx *ctx, const char *key, int value);
+/* Page-locked host memory for frame read-back at full PCIe rate (cudaMallocHost / cudaFreeHost). */
+int pyvr_cuda_host_alloc(size_t bytes, void **out);
+int pyvr_cuda_host_free(void *ptr);
+int pyvr_cuda_device_count(int *count);
+int pyvr_cuda_abi_version(void);
+const char *pyvr_cuda_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYVR_CUDA_H */

@@ -1,0 +1,653 @@
+// abi.cu -- the C ABI of include/pyvr_cuda.h: context, device resources, host-side parameter
+// derivation and launch sequencing.  Stands in for ModernGLManager
+// (pyvr/moderngl_renderer/manager.py) of the reference; the kernels live in march.cu,
+// volume_pack.cu and normals.cu.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+
+using namespace pyvr;
+
+namespace {
+
+thread_local char g_error[512] = "";
+
+int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof g_error, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                                  \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess)                                                                    \
+            return fail(e_ == cudaErrorMemoryAllocation ? PYVR_ERR_NOMEM : PYVR_ERR_CUDA,        \
+                        "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+constexpr int kRing = 3;  // device frame slots used to overlap march and device->host copies
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+}  // namespace
+
+struct pyvr_ctx {
+    int device = 0;
+    int width = 0, height = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
+
+    // volume
+    void *texels = nullptr;
+    size_t texel_bytes = 0;
+    bool half_texels = false;
+    bool have_volume = false;
+    VolumeDesc vol{};
+    float2 *cell_minmax = nullptr;
+    uint8_t *cell_active = nullptr;
+    size_t n_cells = 0;
+    int layout = 1;  // 0 linear, 1 8^3 bricks
+
+    // transfer function
+    float4 *lut = nullptr;
+    int lut_size = 0;
+
+    // camera / params
+    pyvr_view view{};
+    pyvr_params params{};
+    bool have_view = false;
+    bool have_matrices = false;    // set_camera keeps binary32 inverses for the STRICT path
+    float inv_proj[16] = {}, inv_view[16] = {};
+
+    // frame resources
+    pyvr_view *d_views = nullptr;
+    int views_cap = 0;
+    uchar4 *frames = nullptr;      // kRing frames
+    float4 *accum = nullptr;       // one frame, allocated on demand
+    unsigned long long *d_counters = nullptr;
+    unsigned long long *h_counters = nullptr;  // pinned
+    std::vector<cudaEvent_t> ev;   // pairs (start, stop) around march launches
+    cudaEvent_t slot_rendered[kRing] = {}, slot_copied[kRing] = {};
+
+    pyvr_stats stats{};
+};
+
+namespace {
+
+size_t frame_pixels(const pyvr_ctx *c) { return (size_t)c->width * (size_t)c->height; }
+
+// 4x4 inverse in binary64 (Gauss-Jordan, partial pivoting).  m, out: row-major [r][c].
+bool invert4(const double m[4][4], double out[4][4]) {
+    double a[4][8];
+    for (int r = 0; r < 4; ++r)
+        for (int c = 0; c < 4; ++c) {
+            a[r][c] = m[r][c];
+            a[r][4 + c] = r == c ? 1.0 : 0.0;
+        }
+    for (int col = 0; col < 4; ++col) {
+        int piv = col;
+        for (int r = col + 1; r < 4; ++r)
+            if (fabs(a[r][col]) > fabs(a[piv][col])) piv = r;
+        if (a[piv][col] == 0.0) return false;
+        if (piv != col)
+            for (int c = 0; c < 8; ++c) { double t = a[col][c]; a[col][c] = a[piv][c]; a[piv][c] = t; }
+        const double inv = 1.0 / a[col][col];
+        for (int c = 0; c < 8; ++c) a[col][c] *= inv;
+        for (int r = 0; r < 4; ++r) {
+            if (r == col) continue;
+            const double f = a[r][col];
+            if (f != 0.0)
+                for (int c = 0; c < 8; ++c) a[r][c] -= f * a[col][c];
+        }
+    }
+    for (int r = 0; r < 4; ++r)
+        for (int c = 0; c < 4; ++c) out[r][c] = a[r][4 + c];
+    return true;
+}
+
+// GLSL inverse(mat4) evaluated in binary32 by cofactor expansion (column-major m[c*4+r]); the STRICT
+// kernel applies the result per pixel.  Same expression order as the oracle's restatement, so both
+// sides round identically ("Arithmetic contract").
+void inverse4_f32(const float *m, float *o) {
+    const float a00 = m[0], a01 = m[1], a02 = m[2], a03 = m[3], a10 = m[4], a11 = m[5], a12 = m[6], a13 = m[7];
+    const float a20 = m[8], a21 = m[9], a22 = m[10], a23 = m[11], a30 = m[12], a31 = m[13], a32 = m[14], a33 = m[15];
+    const float b00 = a00 * a11 - a01 * a10, b01 = a00 * a12 - a02 * a10, b02 = a00 * a13 - a03 * a10;
+    const float b03 = a01 * a12 - a02 * a11, b04 = a01 * a13 - a03 * a11, b05 = a02 * a13 - a03 * a12;
+    const float b06 = a20 * a31 - a21 * a30, b07 = a20 * a32 - a22 * a30, b08 = a20 * a33 - a23 * a30;
+    const float b09 = a21 * a32 - a22 * a31, b10 = a21 * a33 - a23 * a31, b11 = a22 * a33 - a23 * a32;
+    const float det = b00 * b11 - b01 * b10 + b02 * b09 + b03 * b08 - b04 * b07 + b05 * b06;
+    const float id = 1.0f / det;
+    o[0] = (a11 * b11 - a12 * b10 + a13 * b09) * id;
+    o[1] = (a02 * b10 - a01 * b11 - a03 * b09) * id;
+    o[2] = (a31 * b05 - a32 * b04 + a33 * b03) * id;
+    o[3] = (a22 * b04 - a21 * b05 - a23 * b03) * id;
+    o[4] = (a12 * b08 - a10 * b11 - a13 * b07) * id;
+    o[5] = (a00 * b11 - a02 * b08 + a03 * b07) * id;
+    o[6] = (a32 * b02 - a30 * b05 - a33 * b01) * id;
+    o[7] = (a20 * b05 - a22 * b02 + a23 * b01) * id;
+    o[8] = (a10 * b10 - a11 * b08 + a13 * b06) * id;
+    o[9] = (a01 * b08 - a00 * b10 - a03 * b06) * id;
+    o[10] = (a30 * b04 - a31 * b02 + a33 * b00) * id;
+    o[11] = (a21 * b02 - a20 * b04 - a23 * b00) * id;
+    o[12] = (a11 * b07 - a10 * b09 - a12 * b06) * id;
+    o[13] = (a00 * b09 - a01 * b07 + a02 * b06) * id;
+    o[14] = (a31 * b01 - a30 * b03 - a32 * b00) * id;
+    o[15] = (a20 * b03 - a21 * b01 + a22 * b00) * id;
+}
+
+void fill_volume_desc(pyvr_ctx *c, int shape0, int shape1, int shape2, const float bmin[3], const float bmax[3]) {
+    VolumeDesc &v = c->vol;
+    // GL (width, height, depth) = (shape0, shape1, shape2); width is the memory-fastest axis and is
+    // addressed by tex_coord.x = world z after the shader's swizzle (volume.frag.glsl:90).
+    v.n[0] = shape2; v.n[1] = shape1; v.n[2] = shape0;
+    for (int a = 0; a < 3; ++a) {
+        v.bmin[a] = bmin[a]; v.bmax[a] = bmax[a];
+        const double ext = (double)bmax[a] - (double)bmin[a];
+        v.vscale[a] = (float)((double)v.n[a] / ext);
+        v.voff[a] = (float)(-(double)bmin[a] * (double)v.n[a] / ext - 0.5);
+        v.ncell[a] = (v.n[a] + 7) / 8;
+    }
+    if (c->layout == 1) {
+        const long long nby = v.ncell[1], nbz = v.ncell[2];
+        v.map[0] = {3, 7, nby * nbz * 512, 64};
+        v.map[1] = {3, 7, nbz * 512, 8};
+        v.map[2] = {3, 7, 512, 1};
+    } else {
+        v.map[0] = {31, 0x7fffffff, 0, (long long)v.n[1] * v.n[2]};
+        v.map[1] = {31, 0x7fffffff, 0, (long long)v.n[2]};
+        v.map[2] = {31, 0x7fffffff, 0, 1};
+    }
+}
+
+size_t texel_count(const pyvr_ctx *c) {
+    const VolumeDesc &v = c->vol;
+    if (c->layout == 1) return (size_t)v.ncell[0] * v.ncell[1] * v.ncell[2] * 512;
+    return (size_t)v.n[0] * v.n[1] * v.n[2];
+}
+
+int classify_cells(pyvr_ctx *c) {
+    if (!c->have_volume || c->lut_size <= 0) return PYVR_OK;
+    CU(launch_cell_classify(c->cell_minmax, c->n_cells, c->lut, c->lut_size, c->cell_active, c->stream));
+    return PYVR_OK;
+}
+
+void free_volume(pyvr_ctx *c) {
+    cudaFree(c->texels); c->texels = nullptr;
+    cudaFree(c->cell_minmax); c->cell_minmax = nullptr;
+    cudaFree(c->cell_active); c->cell_active = nullptr;
+    c->have_volume = false;
+    c->vol.texels = nullptr;
+    c->vol.cell_active = nullptr;
+}
+
+int ensure_views(pyvr_ctx *c, int n) {
+    if (n <= c->views_cap) return PYVR_OK;
+    cudaFree(c->d_views);
+    c->d_views = nullptr;
+    c->views_cap = 0;
+    CU(cudaMalloc(&c->d_views, sizeof(pyvr_view) * (size_t)n));
+    c->views_cap = n;
+    return PYVR_OK;
+}
+
+int ensure_events(pyvr_ctx *c, size_t pairs) {
+    while (c->ev.size() < 2 * pairs) {
+        cudaEvent_t e;
+        CU(cudaEventCreate(&e));
+        c->ev.push_back(e);
+    }
+    return PYVR_OK;
+}
+
+MarchArgs make_args(const pyvr_ctx *c) {
+    MarchArgs a{};
+    a.vol = c->vol;
+    a.lut = c->lut;
+    a.lut_size = c->lut_size;
+    a.width = c->width;
+    a.height = c->height;
+    const pyvr_params &p = c->params;
+    a.step = p.step_size;
+    a.ref_step = p.reference_step_size;
+    a.exp2_scale = (float)(-((double)p.step_size / (double)p.reference_step_size) * 1.4426950408889634);
+    a.max_steps = p.max_steps;
+    a.ambient = p.ambient;
+    a.diffuse = p.diffuse;
+    // normalize(light_target - light_position) in binary32, as the shader does (volume.frag.glsl:107)
+    const float lx = p.light_target[0] - p.light_position[0], ly = p.light_target[1] - p.light_position[1],
+                lz = p.light_target[2] - p.light_position[2];
+    const float inv = 1.0f / sqrtf(lx * lx + ly * ly + lz * lz);
+    a.ldir[0] = lx * inv; a.ldir[1] = ly * inv; a.ldir[2] = lz * inv;
+    a.term_alpha = p.termination_alpha;
+    a.flags = p.flags;
+    a.counters = c->d_counters;
+    a.use_matrices = c->have_matrices ? 1 : 0;
+    memcpy(a.inv_proj, c->inv_proj, sizeof a.inv_proj);
+    memcpy(a.inv_view, c->inv_view, sizeof a.inv_view);
+    return a;
+}
+
+// Launch the march for `n` views already resident in c->d_views[first..], timed with events.
+int march(pyvr_ctx *c, int first, int n, uchar4 *out8, float4 *out_acc, size_t ev_pair) {
+    MarchArgs a = make_args(c);
+    a.views = c->d_views + first;
+    a.out8 = out8;
+    a.out_acc = out_acc;
+    CU(cudaEventRecord(c->ev[2 * ev_pair], c->stream));
+    CU(launch_march(a, n, c->half_texels, c->stream));
+    CU(cudaEventRecord(c->ev[2 * ev_pair + 1], c->stream));
+    return PYVR_OK;
+}
+
+int finish_stats(pyvr_ctx *c, size_t pairs, int views) {
+    CU(cudaMemcpyAsync(c->h_counters, c->d_counters, sizeof(unsigned long long) * CNT_N,
+                       cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    float total = 0.0f;
+    for (size_t i = 0; i < pairs; ++i) {
+        float ms = 0.0f;
+        CU(cudaEventElapsedTime(&ms, c->ev[2 * i], c->ev[2 * i + 1]));
+        total += ms;
+    }
+    c->stats.samples = c->h_counters[CNT_SAMPLES];
+    c->stats.samples_fetched = c->h_counters[CNT_FETCHED];
+    c->stats.rays_hit = c->h_counters[CNT_HIT];
+    c->stats.rays_terminated = c->h_counters[CNT_TERM];
+    c->stats.kernel_ms = total;
+    c->stats.kernel_launches = (uint32_t)pairs;
+    c->stats.views = (uint32_t)views;
+    return PYVR_OK;
+}
+
+bool renderable(const pyvr_ctx *c) { return c->have_volume && c->lut_size > 0; }
+
+}  // namespace
+
+extern "C" {
+
+int pyvr_cuda_abi_version(void) { return PYVR_CUDA_ABI_VERSION; }
+
+const char *pyvr_cuda_last_error(void) { return g_error; }
+
+int pyvr_cuda_device_count(int *count) {
+    if (!count) return fail(PYVR_ERR_INVALID, "count is NULL");
+    CU(cudaGetDeviceCount(count));
+    return PYVR_OK;
+}
+
+int pyvr_cuda_create(int device, int width, int height, pyvr_ctx **out_ctx) {
+    if (!out_ctx) return fail(PYVR_ERR_INVALID, "out_ctx is NULL");
+    *out_ctx = nullptr;
+    if (width <= 0 || height <= 0) return fail(PYVR_ERR_INVALID, "viewport %dx%d is not positive", width, height);
+    int n_dev = 0;
+    CU(cudaGetDeviceCount(&n_dev));
+    if (device < 0 || device >= n_dev) return fail(PYVR_ERR_INVALID, "device %d out of range (%d visible)", device, n_dev);
+    DeviceGuard guard(device);
+    pyvr_ctx *c = new (std::nothrow) pyvr_ctx();
+    if (!c) return fail(PYVR_ERR_NOMEM, "out of host memory");
+    c->device = device;
+    c->width = width;
+    c->height = height;
+    const char *layout = getenv("PYVR_CUDA_LAYOUT");
+    if (layout) c->layout = strcmp(layout, "linear") == 0 ? 0 : 1;
+    // defaults of the reference renderer: balanced preset, Light.default(), bounds +-0.5
+    c->params.step_size = 0.01f; c->params.max_steps = 500; c->params.reference_step_size = 0.01f;
+    c->params.ambient = 0.2f; c->params.diffuse = 0.8f;
+    c->params.light_position[0] = c->params.light_position[1] = c->params.light_position[2] = 1.0f;
+    c->params.termination_alpha = 0.99f;
+    c->params.flags = PYVR_FLAG_ESS;
+    cudaError_t e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(&c->frames, frame_pixels(c) * sizeof(uchar4) * kRing);
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_counters, sizeof(unsigned long long) * CNT_N);
+    if (e == cudaSuccess) e = cudaMallocHost(&c->h_counters, sizeof(unsigned long long) * CNT_N);
+    for (int i = 0; i < kRing && e == cudaSuccess; ++i) {
+        e = cudaEventCreateWithFlags(&c->slot_rendered[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->slot_copied[i], cudaEventDisableTiming);
+    }
+    if (e != cudaSuccess) {
+        pyvr_cuda_destroy(c);
+        return fail(e == cudaErrorMemoryAllocation ? PYVR_ERR_NOMEM : PYVR_ERR_CUDA,
+                    "context creation failed: %s", cudaGetErrorString(e));
+    }
+    c->stream = c->own_stream;
+    *out_ctx = c;
+    return PYVR_OK;
+}
+
+int pyvr_cuda_destroy(pyvr_ctx *c) {
+    if (!c) return PYVR_OK;
+    DeviceGuard guard(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+    free_volume(c);
+    cudaFree(c->lut);
+    cudaFree(c->d_views);
+    cudaFree(c->frames);
+    cudaFree(c->accum);
+    cudaFree(c->d_counters);
+    if (c->h_counters) cudaFreeHost(c->h_counters);
+    for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
+    for (int i = 0; i < kRing; ++i) {
+        if (c->slot_rendered[i]) cudaEventDestroy(c->slot_rendered[i]);
+        if (c->slot_copied[i]) cudaEventDestroy(c->slot_copied[i]);
+    }
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    delete c;
+    return PYVR_OK;
+}
+
+int pyvr_cuda_set_stream(pyvr_ctx *c, void *cuda_stream) {
+    if (!c) return fail(PYVR_ERR_INVALID, "ctx is NULL");
+    c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+    return PYVR_OK;
+}
+
+int pyvr_cuda_set_option(pyvr_ctx *c, const char *key, int value) {
+    if (!c || !key) return fail(PYVR_ERR_INVALID, "ctx or key is NULL");
+    if (strcmp(key, "layout") == 0) {
+        if (value != 0 && value != 1) return fail(PYVR_ERR_INVALID, "layout must be 0 (linear) or 1 (bricks)");
+        if (c->have_volume && value != c->layout)
+            return fail(PYVR_ERR_STATE, "layout must be chosen before the volume is uploaded");
+        c->layout = value;
+        return PYVR_OK;
+    }
+    return fail(PYVR_ERR_INVALID, "unknown option '%s'", key);
+}
+
+int pyvr_cuda_upload_volume(pyvr_ctx *c, const float *scalar, const float *normals, int shape0, int shape1,
+                            int shape2, const float bmin[3], const float bmax[3], int texel_format,
+                            int src_is_device) {
+    if (!c || !scalar || !bmin || !bmax) return fail(PYVR_ERR_INVALID, "NULL argument");
+    if (shape0 <= 0 || shape1 <= 0 || shape2 <= 0)
+        return fail(PYVR_ERR_INVALID, "Volume data must be 3D with positive extents, got (%d, %d, %d)", shape0, shape1, shape2);
+    if (texel_format != PYVR_TEXEL_F32X4 && texel_format != PYVR_TEXEL_F16X4)
+        return fail(PYVR_ERR_INVALID, "unknown texel format %d", texel_format);
+    for (int a = 0; a < 3; ++a)
+        if (!(bmax[a] > bmin[a])) return fail(PYVR_ERR_INVALID, "max_bounds must be greater than min_bounds");
+    DeviceGuard guard(c->device);
+    CU(cudaStreamSynchronize(c->stream));
+    free_volume(c);  // the reference leaks the previous textures (manager.py:232-236); not replicated
+
+    c->half_texels = texel_format == PYVR_TEXEL_F16X4;
+    fill_volume_desc(c, shape0, shape1, shape2, bmin, bmax);
+    const size_t voxels = (size_t)shape0 * shape1 * shape2;
+    const size_t n_tex = texel_count(c);
+    c->texel_bytes = n_tex * (c->half_texels ? 8 : 16);
+    c->n_cells = (size_t)c->vol.ncell[0] * c->vol.ncell[1] * c->vol.ncell[2];
+    CU(cudaMalloc(&c->texels, c->texel_bytes));
+    CU(cudaMalloc(&c->cell_minmax, c->n_cells * sizeof(float2)));
+    CU(cudaMalloc(&c->cell_active, c->n_cells));
+    if (n_tex != voxels) CU(cudaMemsetAsync(c->texels, 0, c->texel_bytes, c->stream));
+    c->vol.texels = c->texels;
+    c->vol.cell_active = c->cell_active;
+
+    const float *d_scalar = scalar, *d_normals = normals;
+    float *stage_s = nullptr, *stage_n = nullptr;
+    if (!src_is_device) {
+        CU(cudaMalloc(&stage_s, voxels * sizeof(float)));
+        CU(cudaMemcpyAsync(stage_s, scalar, voxels * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        d_scalar = stage_s;
+        if (normals) {
+            cudaError_t e = cudaMalloc(&stage_n, voxels * 3 * sizeof(float));
+            if (e != cudaSuccess) { cudaFree(stage_s); CU(e); }
+            CU(cudaMemcpyAsync(stage_n, normals, voxels * 3 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+            d_normals = stage_n;
+        }
+    }
+    cudaError_t e = launch_pack_texels(d_scalar, d_normals, c->vol, c->half_texels, c->stream);
+    if (e == cudaSuccess) e = launch_cell_minmax(c->vol, c->half_texels, c->cell_minmax, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(stage_s);
+    cudaFree(stage_n);
+    CU(e);
+    c->have_volume = true;
+    return classify_cells(c);
+}
+
+int pyvr_cuda_set_lut(pyvr_ctx *c, const float *rgba, int size) {
+    if (!c || !rgba) return fail(PYVR_ERR_INVALID, "NULL argument");
+    if (size < 1) return fail(PYVR_ERR_INVALID, "LUT size must be at least 1, got %d", size);
+    if ((size_t)size * sizeof(float4) > 200 * 1024)
+        return fail(PYVR_ERR_INVALID, "LUT of %d entries does not fit in shared memory (max 12800)", size);
+    DeviceGuard guard(c->device);
+    CU(cudaStreamSynchronize(c->stream));
+    if (size != c->lut_size) {
+        cudaFree(c->lut);
+        c->lut = nullptr;
+        c->lut_size = 0;
+        CU(cudaMalloc(&c->lut, (size_t)size * sizeof(float4)));
+    }
+    CU(cudaMemcpyAsync(c->lut, rgba, (size_t)size * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+    c->lut_size = size;
+    CU(cudaStreamSynchronize(c->stream));
+    return classify_cells(c);
+}
+
+int pyvr_cuda_view_from_matrices(const float view[16], const float proj[16], const float cam_pos[3],
+                                 pyvr_view *out) {
+    if (!view || !proj || !cam_pos || !out) return fail(PYVR_ERR_INVALID, "NULL argument");
+    // GL reads the 16 floats column-major: M(r, c) = m[c*4 + r].
+    double V[4][4], P[4][4], iV[4][4], iP[4][4];
+    for (int r = 0; r < 4; ++r)
+        for (int col = 0; col < 4; ++col) {
+            V[r][col] = view[col * 4 + r];
+            P[r][col] = proj[col * 4 + r];
+        }
+    if (!invert4(V, iV)) return fail(PYVR_ERR_INVALID, "view matrix is singular");
+    if (!invert4(P, iP)) return fail(PYVR_ERR_INVALID, "projection matrix is singular");
+    // eye.xy = (inverse(P) * (ndc.x, ndc.y, -1, 1)).xy ; world = inverse(V) * (eye.x, eye.y, -1, 0)
+    const double ex_c = iP[0][3] - iP[0][2], ey_c = iP[1][3] - iP[1][2];
+    for (int r = 0; r < 3; ++r) {
+        out->u[r] = (float)(iV[r][0] * iP[0][0] + iV[r][1] * iP[1][0]);
+        out->v[r] = (float)(iV[r][0] * iP[0][1] + iV[r][1] * iP[1][1]);
+        out->w[r] = (float)(iV[r][0] * ex_c + iV[r][1] * ey_c - iV[r][2]);
+        out->origin[r] = cam_pos[r];
+    }
+    return PYVR_OK;
+}
+
+int pyvr_cuda_set_camera(pyvr_ctx *c, const float view[16], const float proj[16], const float cam_pos[3]) {
+    if (!c) return fail(PYVR_ERR_INVALID, "ctx is NULL");
+    pyvr_view v;
+    int rc = pyvr_cuda_view_from_matrices(view, proj, cam_pos, &v);
+    if (rc != PYVR_OK) return rc;
+    c->view = v;
+    c->have_view = true;
+    inverse4_f32(proj, c->inv_proj);
+    inverse4_f32(view, c->inv_view);
+    c->have_matrices = true;
+    return PYVR_OK;
+}
+
+int pyvr_cuda_set_view(pyvr_ctx *c, const pyvr_view *view) {
+    if (!c || !view) return fail(PYVR_ERR_INVALID, "NULL argument");
+    c->view = *view;
+    c->have_view = true;
+    c->have_matrices = false;
+    return PYVR_OK;
+}
+
+int pyvr_cuda_set_params(pyvr_ctx *c, const pyvr_params *p) {
+    if (!c || !p) return fail(PYVR_ERR_INVALID, "NULL argument");
+    if (!(p->step_size > 0.0f)) return fail(PYVR_ERR_INVALID, "step_size must be positive");
+    if (p->max_steps < 1) return fail(PYVR_ERR_INVALID, "max_steps must be at least 1");
+    if (!(p->reference_step_size > 0.0f)) return fail(PYVR_ERR_INVALID, "reference_step_size must be positive");
+    c->params = *p;
+    return PYVR_OK;
+}
+
+int pyvr_cuda_render_batch(pyvr_ctx *c, const pyvr_view *views, int n, uint8_t *out, int out_is_device) {
+    if (!c || !views || !out) return fail(PYVR_ERR_INVALID, "NULL argument");
+    if (n < 1) return fail(PYVR_ERR_INVALID, "batch of %d views", n);
+    DeviceGuard guard(c->device);
+    const size_t frame_bytes = frame_pixels(c) * sizeof(uchar4);
+    memset(&c->stats, 0, sizeof c->stats);
+    if (!renderable(c)) {  // cleared framebuffer
+        if (out_is_device) {
+            CU(cudaMemsetAsync(out, 0, frame_bytes * n, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+        } else {
+            memset(out, 0, frame_bytes * n);
+        }
+        c->stats.views = (uint32_t)n;
+        return PYVR_OK;
+    }
+    int rc = ensure_views(c, n);
+    if (rc != PYVR_OK) return rc;
+    CU(cudaMemcpyAsync(c->d_views, views, sizeof(pyvr_view) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemsetAsync(c->d_counters, 0, sizeof(unsigned long long) * CNT_N, c->stream));
+
+    size_t pairs = 0;
+    if (out_is_device) {
+        // frames land directly in the caller's device buffer, up to 16 views per launch
+        const int chunk = 16;
+        rc = ensure_events(c, (size_t)(n + chunk - 1) / chunk);
+        if (rc != PYVR_OK) return rc;
+        for (int first = 0; first < n; first += chunk) {
+            const int m = n - first < chunk ? n - first : chunk;
+            rc = march(c, first, m, reinterpret_cast<uchar4 *>(out) + (size_t)first * frame_pixels(c), nullptr, pairs++);
+            if (rc != PYVR_OK) return rc;
+        }
+    } else {
+        // ring of device frames: march(k) overlaps the device->host copy of frame k-1
+        rc = ensure_events(c, (size_t)n);
+        if (rc != PYVR_OK) return rc;
+        for (int k = 0; k < n; ++k) {
+            const int slot = k % kRing;
+            if (k >= kRing) CU(cudaStreamWaitEvent(c->stream, c->slot_copied[slot], 0));
+            uchar4 *frame = c->frames + (size_t)slot * frame_pixels(c);
+            rc = march(c, k, 1, frame, nullptr, pairs++);
+            if (rc != PYVR_OK) return rc;
+            CU(cudaEventRecord(c->slot_rendered[slot], c->stream));
+            CU(cudaStreamWaitEvent(c->copy_stream, c->slot_rendered[slot], 0));
+            CU(cudaMemcpyAsync(out + (size_t)k * frame_bytes, frame, frame_bytes, cudaMemcpyDeviceToHost, c->copy_stream));
+            CU(cudaEventRecord(c->slot_copied[slot], c->copy_stream));
+        }
+        CU(cudaStreamSynchronize(c->copy_stream));
+    }
+    return finish_stats(c, pairs, n);
+}
+
+int pyvr_cuda_render(pyvr_ctx *c, uint8_t *out, int out_is_device) {
+    if (!c || !out) return fail(PYVR_ERR_INVALID, "NULL argument");
+    if (!c->have_view) {  // the reference renders garbage/black without a camera; return the cleared frame
+        DeviceGuard guard(c->device);
+        const size_t frame_bytes = frame_pixels(c) * sizeof(uchar4);
+        memset(&c->stats, 0, sizeof c->stats);
+        if (out_is_device) {
+            CU(cudaMemsetAsync(out, 0, frame_bytes, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+        } else {
+            memset(out, 0, frame_bytes);
+        }
+        return PYVR_OK;
+    }
+    return pyvr_cuda_render_batch(c, &c->view, 1, out, out_is_device);
+}
+
+int pyvr_cuda_render_accum(pyvr_ctx *c, float *out, int out_is_device) {
+    if (!c || !out) return fail(PYVR_ERR_INVALID, "NULL argument");
+    DeviceGuard guard(c->device);
+    const size_t bytes = frame_pixels(c) * sizeof(float4);
+    memset(&c->stats, 0, sizeof c->stats);
+    if (!renderable(c) || !c->have_view) {
+        if (out_is_device) {
+            CU(cudaMemsetAsync(out, 0, bytes, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+        } else {
+            memset(out, 0, bytes);
+        }
+        return PYVR_OK;
+    }
+    float4 *target = reinterpret_cast<float4 *>(out);
+    if (!out_is_device) {
+        if (!c->accum) CU(cudaMalloc(&c->accum, bytes));
+        target = c->accum;
+    }
+    int rc = ensure_views(c, 1);
+    if (rc == PYVR_OK) rc = ensure_events(c, 1);
+    if (rc != PYVR_OK) return rc;
+    CU(cudaMemcpyAsync(c->d_views, &c->view, sizeof(pyvr_view), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemsetAsync(c->d_counters, 0, sizeof(unsigned long long) * CNT_N, c->stream));
+    rc = march(c, 0, 1, nullptr, target, 0);
+    if (rc != PYVR_OK) return rc;
+    if (!out_is_device) CU(cudaMemcpyAsync(out, c->accum, bytes, cudaMemcpyDeviceToHost, c->stream));
+    return finish_stats(c, 1, 1);
+}
+
+int pyvr_cuda_get_stats(pyvr_ctx *c, pyvr_stats *out) {
+    if (!c || !out) return fail(PYVR_ERR_INVALID, "NULL argument");
+    *out = c->stats;
+    return PYVR_OK;
+}
+
+int pyvr_cuda_compute_normals(int device, const float *in, float *out, int n0, int n1, int n2,
+                              int buffers_are_device, float *kernel_ms) {
+    if (!in || !out) return fail(PYVR_ERR_INVALID, "NULL argument");
+    if (n0 <= 0 || n1 <= 0 || n2 <= 0) return fail(PYVR_ERR_INVALID, "Volume data must be 3D with positive extents");
+    int n_dev = 0;
+    CU(cudaGetDeviceCount(&n_dev));
+    if (device < 0 || device >= n_dev) return fail(PYVR_ERR_INVALID, "device %d out of range (%d visible)", device, n_dev);
+    DeviceGuard guard(device);
+    const size_t voxels = (size_t)n0 * n1 * n2;
+    const float *d_in = in;
+    float *d_out = out, *stage_in = nullptr, *stage_out = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaError_t e = cudaSuccess;
+    if (!buffers_are_device) {
+        e = cudaMalloc(&stage_in, voxels * sizeof(float));
+        if (e == cudaSuccess) e = cudaMalloc(&stage_out, voxels * 3 * sizeof(float));
+        if (e == cudaSuccess) e = cudaMemcpy(stage_in, in, voxels * sizeof(float), cudaMemcpyHostToDevice);
+        d_in = stage_in;
+        d_out = stage_out;
+    }
+    if (e == cudaSuccess) e = cudaEventCreate(&e0);
+    if (e == cudaSuccess) e = cudaEventCreate(&e1);
+    if (e == cudaSuccess) e = cudaEventRecord(e0, 0);
+    if (e == cudaSuccess) e = launch_normals(d_in, d_out, n0, n1, n2, 0);
+    if (e == cudaSuccess) e = cudaEventRecord(e1, 0);
+    if (e == cudaSuccess) e = cudaEventSynchronize(e1);
+    if (e == cudaSuccess && kernel_ms) e = cudaEventElapsedTime(kernel_ms, e0, e1);
+    if (e == cudaSuccess && !buffers_are_device)
+        e = cudaMemcpy(out, stage_out, voxels * 3 * sizeof(float), cudaMemcpyDeviceToHost);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    cudaFree(stage_in);
+    cudaFree(stage_out);
+    CU(e);
+    return PYVR_OK;
+}
+
+int pyvr_cuda_host_alloc(size_t bytes, void **out) {
+    if (!out) return fail(PYVR_ERR_INVALID, "out is NULL");
+    CU(cudaMallocHost(out, bytes));
+    return PYVR_OK;
+}
+
+int pyvr_cuda_host_free(void *p) {
+    if (p) CU(cudaFreeHost(p));
+    return PYVR_OK;
+}
+
+}  // extern "C"

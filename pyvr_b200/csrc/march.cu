@@ -1,0 +1,320 @@
+// march.cu -- K1: the volume ray-march kernel (sm_100a).
+//
+// Replaces the fragment shader pyvr/shaders/volume.frag.glsl:70-122 of the reference together with the
+// fixed-function stages after it: blend SRC_ALPHA/ONE_MINUS_SRC_ALPHA onto a cleared target
+// (pyvr/moderngl_renderer/manager.py:217-220), RGBA8 quantisation (manager.py:29) and the bottom-up
+// row order of fbo.read (manager.py:228-230).
+//
+// Mapping: one thread per ray; a warp owns an 8x4 pixel tile, a CTA (4 warps) a 16x8 tile, so the 8
+// texel gathers of neighbouring rays land in the same 128-byte lines of the packed {s,nx,ny,nz}
+// texel array (L1 does the gather amplification, L2/HBM stream each touched line once).  The RGBA
+// transfer-function LUT is staged in shared memory once per CTA.
+//
+// Two arithmetic modes (MarchArgs.flags):
+//   STRICT  statement-by-statement twin of the oracle: incremental position p += dir*step, IEEE
+//           divide / sqrt / expf, no skipping.  Used to pin the kernel against oracle/pyvr_oracle.c.
+//   fast    (default) the same sample lattice evaluated directly in voxel space
+//           x(i) = X0 + i*DX (one FMA per axis), ex2.approx / rsqrt.approx, optional exact
+//           empty-space skipping over 8^3 macrocells.  Differences to STRICT are ~1e-6 relative.
+#include "common.cuh"
+
+namespace pyvr {
+namespace {
+
+constexpr int TILE_W = 16, TILE_H = 8, CTA_THREADS = TILE_W * TILE_H;
+
+struct Taps {
+    int i0, i1;
+    float f;
+};
+
+// One axis of a LINEAR / CLAMP_TO_EDGE fetch: texel centres at integer + 0.5 (GL 3.3 spec 3.8.8).
+__device__ __forceinline__ Taps axis_taps(float u, int n) {
+    float x = u * (float)n - 0.5f;
+    float fl = floorf(x);
+    Taps t;
+    t.f = x - fl;
+    int i = (int)fl;
+    t.i0 = min(max(i, 0), n - 1);
+    t.i1 = min(max(i + 1, 0), n - 1);
+    return t;
+}
+
+// Same, from a voxel-space coordinate already known to lie in [-0.5, n-0.5].
+__device__ __forceinline__ Taps voxel_taps(float x, int n) {
+    float fl = floorf(x);
+    Taps t;
+    t.f = x - fl;
+    int i = (int)fl;
+    t.i0 = max(i, 0);
+    t.i1 = min(i + 1, n - 1);
+    return t;
+}
+
+__device__ __forceinline__ long long axis_offset(const AxisMap &m, int i) {
+    return (long long)(i >> m.shift) * m.outer + (long long)(i & m.mask) * m.inner;
+}
+
+__device__ __forceinline__ float lerpf(float a, float b, float t) { return fmaf(t, b - a, a); }
+
+template <bool HALF>
+__device__ __forceinline__ float4 load_texel(const void *base, long long idx) {
+    if constexpr (HALF) {
+        uint2 raw = __ldg(reinterpret_cast<const uint2 *>(base) + idx);
+        __half2 a = *reinterpret_cast<__half2 *>(&raw.x), b = *reinterpret_cast<__half2 *>(&raw.y);
+        float2 fa = __half22float2(a), fb = __half22float2(b);
+        return make_float4(fa.x, fa.y, fb.x, fb.y);
+    } else {
+        return __ldg(reinterpret_cast<const float4 *>(base) + idx);
+    }
+}
+
+struct Corner8 {
+    float4 c[8];  // index = (x_tap << 2) | (y_tap << 1) | z_tap
+};
+
+template <bool HALF>
+__device__ __forceinline__ Corner8 gather(const VolumeDesc &v, const Taps &tx, const Taps &ty, const Taps &tz) {
+    long long ox0 = axis_offset(v.map[0], tx.i0), ox1 = axis_offset(v.map[0], tx.i1);
+    long long oy0 = axis_offset(v.map[1], ty.i0), oy1 = axis_offset(v.map[1], ty.i1);
+    long long oz0 = axis_offset(v.map[2], tz.i0), oz1 = axis_offset(v.map[2], tz.i1);
+    long long b00 = ox0 + oy0, b01 = ox0 + oy1, b10 = ox1 + oy0, b11 = ox1 + oy1;
+    Corner8 r;
+    r.c[0] = load_texel<HALF>(v.texels, b00 + oz0);
+    r.c[1] = load_texel<HALF>(v.texels, b00 + oz1);
+    r.c[2] = load_texel<HALF>(v.texels, b01 + oz0);
+    r.c[3] = load_texel<HALF>(v.texels, b01 + oz1);
+    r.c[4] = load_texel<HALF>(v.texels, b10 + oz0);
+    r.c[5] = load_texel<HALF>(v.texels, b10 + oz1);
+    r.c[6] = load_texel<HALF>(v.texels, b11 + oz0);
+    r.c[7] = load_texel<HALF>(v.texels, b11 + oz1);
+    return r;
+}
+
+// Filter order of the oracle: GL x (= world z, the fastest axis) first, then GL y (world y), then GL z (world x).
+#define PYVR_TRILERP(field)                                                                       \
+    lerpf(lerpf(lerpf(k.c[0].field, k.c[1].field, wz), lerpf(k.c[2].field, k.c[3].field, wz), wy), \
+          lerpf(lerpf(k.c[4].field, k.c[5].field, wz), lerpf(k.c[6].field, k.c[7].field, wz), wy), wx)
+
+__device__ __forceinline__ float clamp01(float v) { return fminf(fmaxf(v, 0.0f), 1.0f); }
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+struct Accum {
+    float r, g, b, a;
+};
+
+// Shade + composite one sample (volume.frag.glsl:96-115).  `k` holds the 8 corner texels.
+template <bool STRICT>
+__device__ __forceinline__ void shade(const MarchArgs &a, const float4 *s_lut, const Corner8 &k,
+                                      float wx, float wy, float wz, Accum &acc) {
+    const float density = PYVR_TRILERP(x);
+    // texture(transfer_function_lut, vec2(density, 0.5)): linear, clamp-to-edge, row axis degenerate
+    const Taps tl = axis_taps(density, a.lut_size);
+    const float4 l0 = s_lut[tl.i0], l1 = s_lut[tl.i1];
+    const float alpha_tf = lerpf(l0.w, l1.w, tl.f);
+    if (!STRICT && alpha_tf == 0.0f) return;  // contributes exactly +0 to every accumulator
+    float alpha;
+    if (STRICT) alpha = 1.0f - expf(-alpha_tf * a.step / a.ref_step);
+    else alpha = 1.0f - ex2_approx(alpha_tf * a.exp2_scale);
+    const float cr = lerpf(l0.x, l1.x, tl.f), cg = lerpf(l0.y, l1.y, tl.f), cb = lerpf(l0.z, l1.z, tl.f);
+    float nx = PYVR_TRILERP(y), ny = PYVR_TRILERP(z), nz = PYVR_TRILERP(w);
+    float inv;
+    if (STRICT) inv = 1.0f / sqrtf(nx * nx + ny * ny + nz * nz);
+    else inv = rsqrtf(fmaf(nz, nz, fmaf(ny, ny, nx * nx)));
+    nx *= inv; ny *= inv; nz *= inv;
+    float ndotl;
+    if (STRICT) ndotl = nx * a.ldir[0] + ny * a.ldir[1] + nz * a.ldir[2];
+    else ndotl = fmaf(nz, a.ldir[2], fmaf(ny, a.ldir[1], nx * a.ldir[0]));
+    // fmaxf(NaN, 0) = 0: a zero-length normal gives the ambient term only (oracle header).
+    const float diff = fmaxf(ndotl, 0.0f);
+    const float light = STRICT ? a.ambient + a.diffuse * diff : fmaf(a.diffuse, diff, a.ambient);
+    const float t = 1.0f - acc.a;
+    acc.r = fmaf(t, cr * light * alpha, acc.r);
+    acc.g = fmaf(t, cg * light * alpha, acc.g);
+    acc.b = fmaf(t, cb * light * alpha, acc.b);
+    acc.a = fmaf(t, alpha, acc.a);
+}
+
+template <bool STRICT, bool HALF>
+__global__ void __launch_bounds__(CTA_THREADS)
+march_kernel(const __grid_constant__ MarchArgs a) {
+    extern __shared__ float4 s_lut[];
+    for (int i = threadIdx.x; i < a.lut_size; i += CTA_THREADS) s_lut[i] = a.lut[i];
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int px = blockIdx.x * TILE_W + (warp & 1) * 8 + (lane & 7);
+    const int py = blockIdx.y * TILE_H + (warp >> 1) * 4 + (lane >> 3);
+    const bool in_image = px < a.width && py < a.height;
+    const pyvr_view vw = a.views[blockIdx.z];
+    const VolumeDesc &vol = a.vol;
+
+    Accum acc = {0.0f, 0.0f, 0.0f, 0.0f};
+    unsigned n_samples = 0, n_fetched = 0;
+    bool hit = false, terminated = false;
+
+    if (in_image && vol.texels != nullptr && a.lut_size > 0) {
+        // volume.vert.glsl:8 at the pixel centre, volume.frag.glsl:33-35,47-54 in closed form
+        const float ndx = ((float)px + 0.5f) / (float)a.width * 2.0f - 1.0f;
+        const float ndy = ((float)py + 0.5f) / (float)a.height * 2.0f - 1.0f;
+        float dx, dy, dz;
+        if (STRICT && a.use_matrices) {
+            // eye = inverse(P) * (ndc, -1, 1); eye.zw = (-1, 0); world = inverse(V) * eye
+            const float *ip = a.inv_proj, *iv = a.inv_view;
+            const float ex = ip[0] * ndx + ip[4] * ndy + ip[8] * -1.0f + ip[12] * 1.0f;
+            const float ey = ip[1] * ndx + ip[5] * ndy + ip[9] * -1.0f + ip[13] * 1.0f;
+            dx = iv[0] * ex + iv[4] * ey + iv[8] * -1.0f + iv[12] * 0.0f;
+            dy = iv[1] * ex + iv[5] * ey + iv[9] * -1.0f + iv[13] * 0.0f;
+            dz = iv[2] * ex + iv[6] * ey + iv[10] * -1.0f + iv[14] * 0.0f;
+        } else {
+            dx = fmaf(vw.u[0], ndx, fmaf(vw.v[0], ndy, vw.w[0]));
+            dy = fmaf(vw.u[1], ndx, fmaf(vw.v[1], ndy, vw.w[1]));
+            dz = fmaf(vw.u[2], ndx, fmaf(vw.v[2], ndy, vw.w[2]));
+        }
+        const float dinv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
+        dx *= dinv; dy *= dinv; dz *= dinv;
+        const float ox = vw.origin[0], oy = vw.origin[1], oz = vw.origin[2];
+
+        // intersect_box, volume.frag.glsl:56-68 (IEEE divide: 1/0 = inf is relied on)
+        const float ix = 1.0f / dx, iy = 1.0f / dy, iz = 1.0f / dz;
+        const float ax = (vol.bmin[0] - ox) * ix, bx = (vol.bmax[0] - ox) * ix;
+        const float ay = (vol.bmin[1] - oy) * iy, by = (vol.bmax[1] - oy) * iy;
+        const float az = (vol.bmin[2] - oz) * iz, bz = (vol.bmax[2] - oz) * iz;
+        float t_near = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
+        const float t_far = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+        hit = t_near <= t_far && t_far > 0.0f;
+
+        if (hit) {
+            t_near = fmaxf(t_near, 0.0f);
+            // The shader runs to max_steps; everything past t_far + 2 steps is outside the box
+            // (the validity test below still decides every sample), so stop there.
+            const float span = (t_far - t_near) / a.step;
+            const int n_steps = (int)fminf((float)a.max_steps, ceilf(span) + 2.0f);
+            const float p0x = ox + dx * t_near, p0y = oy + dy * t_near, p0z = oz + dz * t_near;
+            const float sx = dx * a.step, sy = dy * a.step, sz = dz * a.step;
+
+            if (STRICT) {
+                float pxw = p0x, pyw = p0y, pzw = p0z;
+                int i = 0;
+                for (; i < n_steps && acc.a < a.term_alpha; ++i) {
+                    const float tcx = (pxw - vol.bmin[0]) / (vol.bmax[0] - vol.bmin[0]);
+                    const float tcy = (pyw - vol.bmin[1]) / (vol.bmax[1] - vol.bmin[1]);
+                    const float tcz = (pzw - vol.bmin[2]) / (vol.bmax[2] - vol.bmin[2]);
+                    if (tcx >= 0.0f && tcx <= 1.0f && tcy >= 0.0f && tcy <= 1.0f && tcz >= 0.0f && tcz <= 1.0f) {
+                        ++n_samples; ++n_fetched;
+                        const Taps tx = axis_taps(tcx, vol.n[0]), ty = axis_taps(tcy, vol.n[1]),
+                                   tz = axis_taps(tcz, vol.n[2]);
+                        const Corner8 k = gather<HALF>(vol, tx, ty, tz);
+                        shade<true>(a, s_lut, k, tx.f, ty.f, tz.f, acc);
+                    }
+                    pxw += sx; pyw += sy; pzw += sz;
+                }
+                terminated = (i < n_steps) || (n_steps < a.max_steps && acc.a >= a.term_alpha);
+            } else {
+                // voxel-space lattice: x(i) = X0 + i*DX, valid iff -0.5 <= x <= n-0.5 on every axis
+                const float X0 = fmaf(p0x, vol.vscale[0], vol.voff[0]), DX = sx * vol.vscale[0];
+                const float Y0 = fmaf(p0y, vol.vscale[1], vol.voff[1]), DY = sy * vol.vscale[1];
+                const float Z0 = fmaf(p0z, vol.vscale[2], vol.voff[2]), DZ = sz * vol.vscale[2];
+                const float hx = (float)vol.n[0] - 0.5f, hy = (float)vol.n[1] - 0.5f, hz = (float)vol.n[2] - 0.5f;
+                const bool ess = (a.flags & PYVR_FLAG_ESS) && vol.cell_active != nullptr;
+                const float rDX = 1.0f / DX, rDY = 1.0f / DY, rDZ = 1.0f / DZ;
+                int i = 0;
+                while (i < n_steps) {
+                    const float fi = (float)i;
+                    const float x = fmaf(fi, DX, X0), y = fmaf(fi, DY, Y0), z = fmaf(fi, DZ, Z0);
+                    if (x >= -0.5f && x <= hx && y >= -0.5f && y <= hy && z >= -0.5f && z <= hz) {
+                        const Taps tx = voxel_taps(x, vol.n[0]), ty = voxel_taps(y, vol.n[1]),
+                                   tz = voxel_taps(z, vol.n[2]);
+                        if (ess) {
+                            const int cx = tx.i0 >> 3, cy = ty.i0 >> 3, cz = tz.i0 >> 3;
+                            const uint8_t active =
+                                __ldg(vol.cell_active + ((size_t)cx * vol.ncell[1] + cy) * vol.ncell[2] + cz);
+                            if (!active) {
+                                // whole steps that stay inside this cell on every axis (conservative by 0.01 step)
+                                const float ex = ((DX > 0.0f ? (float)(8 * cx + 8) : (float)(8 * cx)) - x) * rDX;
+                                const float ey = ((DY > 0.0f ? (float)(8 * cy + 8) : (float)(8 * cy)) - y) * rDY;
+                                const float ez = ((DZ > 0.0f ? (float)(8 * cz + 8) : (float)(8 * cz)) - z) * rDZ;
+                                // a zero direction component gives +-inf or NaN: fminf ignores NaN, inf never wins
+                                float tmin = fminf(fminf(DX != 0.0f ? ex : 3.0e38f, DY != 0.0f ? ey : 3.0e38f),
+                                                   DZ != 0.0f ? ez : 3.0e38f);
+                                int skip = (int)fminf(floorf(tmin - 0.01f), (float)(n_steps - i));
+                                skip = max(skip, 1);
+                                n_samples += skip;
+                                i += skip;
+                                continue;
+                            }
+                        }
+                        ++n_samples; ++n_fetched;
+                        const Corner8 k = gather<HALF>(vol, tx, ty, tz);
+                        shade<false>(a, s_lut, k, tx.f, ty.f, tz.f, acc);
+                        if (acc.a >= a.term_alpha) { terminated = true; break; }
+                    }
+                    ++i;
+                }
+                if (terminated && i + 1 >= a.max_steps) terminated = false;
+            }
+        }
+    }
+
+    // fragment colour -> [0,1] clamp -> blend onto the (0,0,0,0) clear -> clamp -> round to RGBA8
+    if (in_image) {
+        const size_t pix = ((size_t)blockIdx.z * a.height + py) * a.width + px;
+        if (a.out_acc) a.out_acc[pix] = make_float4(acc.r, acc.g, acc.b, acc.a);
+        if (a.out8) {
+            const float al = clamp01(acc.a);
+            float r = clamp01(acc.r), g = clamp01(acc.g), b = clamp01(acc.b), o = al;
+            if (!(a.flags & PYVR_FLAG_NO_BLEND)) { r *= al; g *= al; b *= al; o = al * al; }
+            uchar4 q;
+            q.x = (unsigned char)__float2uint_rn(clamp01(r) * 255.0f);
+            q.y = (unsigned char)__float2uint_rn(clamp01(g) * 255.0f);
+            q.z = (unsigned char)__float2uint_rn(clamp01(b) * 255.0f);
+            q.w = (unsigned char)__float2uint_rn(clamp01(o) * 255.0f);
+            a.out8[pix] = q;
+        }
+    }
+
+    // per-warp reduction of the work counters, one atomic per counter per warp
+    if (a.counters) {
+        unsigned s = n_samples, f = n_fetched;
+        for (int o = 16; o > 0; o >>= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, o);
+            f += __shfl_xor_sync(0xffffffffu, f, o);
+        }
+        const unsigned h = __popc(__ballot_sync(0xffffffffu, hit));
+        const unsigned t = __popc(__ballot_sync(0xffffffffu, terminated));
+        if (lane == 0) {
+            if (s) atomicAdd(a.counters + CNT_SAMPLES, (unsigned long long)s);
+            if (f) atomicAdd(a.counters + CNT_FETCHED, (unsigned long long)f);
+            if (h) atomicAdd(a.counters + CNT_HIT, (unsigned long long)h);
+            if (t) atomicAdd(a.counters + CNT_TERM, (unsigned long long)t);
+        }
+    }
+}
+
+template <bool STRICT, bool HALF>
+cudaError_t launch_one(const MarchArgs &a, int n_views, cudaStream_t stream) {
+    const size_t smem = (size_t)a.lut_size * sizeof(float4);
+    auto kern = march_kernel<STRICT, HALF>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    dim3 grid((a.width + TILE_W - 1) / TILE_W, (a.height + TILE_H - 1) / TILE_H, n_views);
+    kern<<<grid, CTA_THREADS, smem, stream>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_march(const MarchArgs &a, int n_views, bool half_texels, cudaStream_t stream) {
+    const bool strict = (a.flags & PYVR_FLAG_STRICT) != 0;
+    if (strict) return half_texels ? launch_one<true, true>(a, n_views, stream) : launch_one<true, false>(a, n_views, stream);
+    return half_texels ? launch_one<false, true>(a, n_views, stream) : launch_one<false, false>(a, n_views, stream);
+}
+
+}  // namespace pyvr

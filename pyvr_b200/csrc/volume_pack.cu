@@ -1,0 +1,155 @@
+// volume_pack.cu -- device-side preparation of the volume the march kernel samples.
+//
+//  * pack_texels: fuses the reference's two textures (R32F scalar, RGB32F normal;
+//    pyvr/moderngl_renderer/manager.py:95-101,123-129) into one interleaved texel {s,nx,ny,nz}
+//    (binary32 or binary16) stored in the separable (linear or 8^3-brick) layout of VolumeDesc.
+//    A Volume without normals is packed with normal = (s, 0, 0): that is what the shader samples when
+//    `normal_volume` is left on texture unit 0 (renderer.py:143-146).
+//  * cell_minmax / cell_classify: the macrocell grid for exact empty-space skipping.  A cell is
+//    inactive only if every sample whose lower taps fall in it provably has alpha_tf == 0.
+#include "common.cuh"
+
+namespace pyvr {
+namespace {
+
+__device__ __forceinline__ long long axis_offset(const AxisMap &m, int i) {
+    return (long long)(i >> m.shift) * m.outer + (long long)(i & m.mask) * m.inner;
+}
+
+// One thread per source voxel, z (memory-fastest in the source) across threadIdx.x: reads are
+// coalesced; writes are coalesced within a brick row (8 texels = 128 B for f32x4) or fully (linear).
+template <bool HALF>
+__global__ void __launch_bounds__(256)
+pack_texels_kernel(const float *__restrict__ scalar, const float *__restrict__ normals, VolumeDesc v) {
+    const int nz = v.n[2], ny = v.n[1], nx = v.n[0];
+    const long long total = (long long)nx * ny * nz;
+    for (long long flat = (long long)blockIdx.x * blockDim.x + threadIdx.x; flat < total;
+         flat += (long long)gridDim.x * blockDim.x) {
+        const int iz = (int)(flat % nz);
+        const long long rest = flat / nz;
+        const int iy = (int)(rest % ny), ix = (int)(rest / ny);
+        const float s = scalar[flat];
+        float a, b, c;
+        if (normals) {
+            a = normals[3 * flat + 0]; b = normals[3 * flat + 1]; c = normals[3 * flat + 2];
+        } else {
+            a = s; b = 0.0f; c = 0.0f;
+        }
+        const long long at = axis_offset(v.map[0], ix) + axis_offset(v.map[1], iy) + axis_offset(v.map[2], iz);
+        if constexpr (HALF) {
+            __half2 lo = __floats2half2_rn(s, a), hi = __floats2half2_rn(b, c);
+            uint2 raw;
+            raw.x = *reinterpret_cast<unsigned *>(&lo);
+            raw.y = *reinterpret_cast<unsigned *>(&hi);
+            reinterpret_cast<uint2 *>(const_cast<void *>(v.texels))[at] = raw;
+        } else {
+            reinterpret_cast<float4 *>(const_cast<void *>(v.texels))[at] = make_float4(s, a, b, c);
+        }
+    }
+}
+
+template <bool HALF>
+__device__ __forceinline__ float load_scalar(const void *base, long long idx) {
+    if constexpr (HALF) return __half2float(reinterpret_cast<const __half *>(base)[4 * idx]);
+    else return reinterpret_cast<const float *>(base)[4 * idx];
+}
+
+// One warp per macrocell: min/max of the scalar over texels [8c, min(8c+8, n-1)]^3 -- the cell's own
+// 8^3 voxels plus the +1 apron that the upper trilinear taps of its samples can reach.
+template <bool HALF>
+__global__ void __launch_bounds__(256)
+cell_minmax_kernel(VolumeDesc v, float2 *__restrict__ out) {
+    const long long n_cells = (long long)v.ncell[0] * v.ncell[1] * v.ncell[2];
+    const int lane = threadIdx.x & 31;
+    for (long long cell = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; cell < n_cells;
+         cell += ((long long)gridDim.x * blockDim.x) >> 5) {
+        const int cz = (int)(cell % v.ncell[2]);
+        const long long r = cell / v.ncell[2];
+        const int cy = (int)(r % v.ncell[1]), cx = (int)(r / v.ncell[1]);
+        const int x0 = 8 * cx, y0 = 8 * cy, z0 = 8 * cz;
+        const int wx = min(x0 + 8, v.n[0] - 1) - x0 + 1, wy = min(y0 + 8, v.n[1] - 1) - y0 + 1,
+                  wz = min(z0 + 8, v.n[2] - 1) - z0 + 1;
+        float lo = INFINITY, hi = -INFINITY;
+        for (int t = lane; t < wx * wy * wz; t += 32) {
+            const int dz = t % wz, dy = (t / wz) % wy, dx = t / (wz * wy);
+            const long long at = axis_offset(v.map[0], x0 + dx) + axis_offset(v.map[1], y0 + dy) +
+                                 axis_offset(v.map[2], z0 + dz);
+            const float s = load_scalar<HALF>(v.texels, at);
+            // NaN voxels: keep the cell active by poisoning the range
+            if (s != s) { lo = -INFINITY; hi = INFINITY; }
+            lo = fminf(lo, s); hi = fmaxf(hi, s);
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+            hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        }
+        if (lane == 0) out[cell] = make_float2(lo, hi);
+    }
+}
+
+// LUT taps a density can select: x = d*size - 0.5, taps floor(x), floor(x)+1, both clamped.  The cell
+// is inactive iff every LUT alpha in the tap range of [lo, hi], widened by one entry on each side
+// for binary32 slop in the trilinear filter, is exactly zero.
+__global__ void __launch_bounds__(256)
+cell_classify_kernel(const float2 *__restrict__ mm, size_t n_cells, const float4 *__restrict__ lut,
+                     int lut_size, uint8_t *__restrict__ active) {
+    extern __shared__ int s_nonzero_before[];  // [j] = number of nonzero alphas in lut[0..j)
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int j = 0; j < lut_size; ++j) {
+            s_nonzero_before[j] = run;
+            run += (lut[j].w != 0.0f) ? 1 : 0;  // NaN != 0 is true: stays active
+        }
+        s_nonzero_before[lut_size] = run;
+    }
+    __syncthreads();
+    for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_cells;
+         c += (size_t)gridDim.x * blockDim.x) {
+        const float2 r = mm[c];
+        const float size = (float)lut_size;
+        float xl = floorf(r.x * size - 0.5f) - 1.0f, xh = floorf(r.y * size - 0.5f) + 2.0f;
+        const int jl = (int)fminf(fmaxf(xl, 0.0f), size - 1.0f);
+        const int jh = (int)fminf(fmaxf(xh, 0.0f), size - 1.0f);
+        active[c] = (s_nonzero_before[jh + 1] - s_nonzero_before[jl]) != 0 ? 1 : 0;
+    }
+}
+
+inline int grid_for(long long work, int block, int max_blocks = 148 * 16) {
+    long long g = (work + block - 1) / block;
+    return (int)(g < 1 ? 1 : (g > max_blocks ? max_blocks : g));
+}
+
+}  // namespace
+
+cudaError_t launch_pack_texels(const float *scalar, const float *normals, const VolumeDesc &vol,
+                               bool half_texels, cudaStream_t stream) {
+    const long long total = (long long)vol.n[0] * vol.n[1] * vol.n[2];
+    const int grid = grid_for(total, 256);
+    if (half_texels) pack_texels_kernel<true><<<grid, 256, 0, stream>>>(scalar, normals, vol);
+    else pack_texels_kernel<false><<<grid, 256, 0, stream>>>(scalar, normals, vol);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_cell_minmax(const VolumeDesc &vol, bool half_texels, float2 *cell_minmax,
+                               cudaStream_t stream) {
+    const long long n_cells = (long long)vol.ncell[0] * vol.ncell[1] * vol.ncell[2];
+    const int grid = grid_for(n_cells * 32, 256);
+    if (half_texels) cell_minmax_kernel<true><<<grid, 256, 0, stream>>>(vol, cell_minmax);
+    else cell_minmax_kernel<false><<<grid, 256, 0, stream>>>(vol, cell_minmax);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_cell_classify(const float2 *cell_minmax, size_t n_cells, const float4 *lut,
+                                 int lut_size, uint8_t *cell_active, cudaStream_t stream) {
+    const int grid = grid_for((long long)n_cells, 256, 148 * 4);
+    const size_t smem = (size_t)(lut_size + 1) * sizeof(int);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(cell_classify_kernel,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    cell_classify_kernel<<<grid, 256, smem, stream>>>(cell_minmax, n_cells, lut, lut_size, cell_active);
+    return cudaGetLastError();
+}
+
+}  // namespace pyvr

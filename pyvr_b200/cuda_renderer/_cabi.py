@@ -1,0 +1,169 @@
+"""ctypes binding of ``libpyvr_cuda.so`` (the C ABI declared in ``include/pyvr_cuda.h``).
+
+The library is built in-tree by :func:`pyvr_b200._build.build_library` (``nvcc`` for sm_100a).  There
+is no CPU fallback: if the library cannot be loaded, or no CUDA device is visible, every compute
+entry point raises ``RuntimeError``.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional
+
+import numpy as np
+
+PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(PKG_DIR, "libpyvr_cuda.so")
+
+ABI_VERSION = 1
+TEXEL_F32X4, TEXEL_F16X4 = 0, 1
+FLAG_STRICT, FLAG_ESS, FLAG_NO_BLEND = 0x1, 0x2, 0x4
+
+# name -> (restype, argtypes); every symbol include/pyvr_cuda.h declares
+_c = ctypes
+_vp, _i, _fp = _c.c_void_p, _c.c_int, _c.POINTER(_c.c_float)
+
+
+class View(ctypes.Structure):
+    """``pyvr_view``: ray origin and the basis of ``dir = normalize(u*ndc.x + v*ndc.y + w)``."""
+    _fields_ = [("origin", _c.c_float * 3), ("u", _c.c_float * 3), ("v", _c.c_float * 3), ("w", _c.c_float * 3)]
+
+
+class Params(ctypes.Structure):
+    """``pyvr_params``: the shader's non-camera uniforms."""
+    _fields_ = [
+        ("step_size", _c.c_float), ("max_steps", _c.c_int32), ("reference_step_size", _c.c_float),
+        ("ambient", _c.c_float), ("diffuse", _c.c_float),
+        ("light_position", _c.c_float * 3), ("light_target", _c.c_float * 3),
+        ("termination_alpha", _c.c_float), ("flags", _c.c_uint32),
+    ]
+
+
+class Stats(ctypes.Structure):
+    """``pyvr_stats``."""
+    _fields_ = [
+        ("samples", _c.c_uint64), ("samples_fetched", _c.c_uint64), ("rays_hit", _c.c_uint64),
+        ("rays_terminated", _c.c_uint64), ("kernel_ms", _c.c_float),
+        ("kernel_launches", _c.c_uint32), ("views", _c.c_uint32),
+    ]
+
+    def as_dict(self) -> dict:
+        return {name: getattr(self, name) for name, _ in self._fields_}
+
+
+SYMBOLS = {
+    "pyvr_cuda_create": (_i, [_i, _i, _i, _c.POINTER(_vp)]),
+    "pyvr_cuda_destroy": (_i, [_vp]),
+    "pyvr_cuda_set_stream": (_i, [_vp, _vp]),
+    "pyvr_cuda_upload_volume": (_i, [_vp, _vp, _vp, _i, _i, _i, _fp, _fp, _i, _i]),
+    "pyvr_cuda_set_lut": (_i, [_vp, _vp, _i]),
+    "pyvr_cuda_set_camera": (_i, [_vp, _fp, _fp, _fp]),
+    "pyvr_cuda_view_from_matrices": (_i, [_fp, _fp, _fp, _c.POINTER(View)]),
+    "pyvr_cuda_set_view": (_i, [_vp, _c.POINTER(View)]),
+    "pyvr_cuda_set_params": (_i, [_vp, _c.POINTER(Params)]),
+    "pyvr_cuda_render": (_i, [_vp, _vp, _i]),
+    "pyvr_cuda_render_batch": (_i, [_vp, _vp, _i, _vp, _i]),
+    "pyvr_cuda_render_accum": (_i, [_vp, _vp, _i]),
+    "pyvr_cuda_get_stats": (_i, [_vp, _c.POINTER(Stats)]),
+    "pyvr_cuda_compute_normals": (_i, [_i, _vp, _vp, _i, _i, _i, _i, _fp]),
+    "pyvr_cuda_set_option": (_i, [_vp, _c.c_char_p, _i]),
+    "pyvr_cuda_host_alloc": (_i, [_c.c_size_t, _c.POINTER(_vp)]),
+    "pyvr_cuda_host_free": (_i, [_vp]),
+    "pyvr_cuda_device_count": (_i, [_c.POINTER(_i)]),
+    "pyvr_cuda_abi_version": (_i, []),
+    "pyvr_cuda_last_error": (_c.c_char_p, []),
+}
+
+_lib = None
+
+
+def lib():
+    """Load ``libpyvr_cuda.so`` (once) and declare every prototype.  Raises if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  pyvr_b200 has no CPU fallback.")
+    handle = ctypes.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in SYMBOLS.items():
+        fn = getattr(handle, name)
+        fn.restype, fn.argtypes = restype, argtypes
+    if handle.pyvr_cuda_abi_version() != ABI_VERSION:
+        raise RuntimeError("libpyvr_cuda.so ABI version mismatch; rebuild the library")
+    _lib = handle
+    return _lib
+
+
+def last_error() -> str:
+    msg = lib().pyvr_cuda_last_error()
+    return msg.decode(errors="replace") if msg else ""
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise RuntimeError(f"pyvr_cuda error {rc}: {last_error()}")
+
+
+def device_count() -> int:
+    n = _c.c_int(0)
+    check(lib().pyvr_cuda_device_count(_c.byref(n)))
+    return n.value
+
+
+def f32_ptr(a: np.ndarray):
+    return a.ctypes.data_as(_fp)
+
+
+def vec3(values) -> np.ndarray:
+    a = np.ascontiguousarray(np.asarray(values, dtype=np.float32).reshape(3))
+    return a
+
+
+def view_from_matrices(view: np.ndarray, proj: np.ndarray, cam_pos) -> View:
+    """``pyvr_view`` from the reference's three camera uniforms (matrices as ``.tobytes()`` order)."""
+    v = np.ascontiguousarray(view, dtype=np.float32).reshape(16)
+    p = np.ascontiguousarray(proj, dtype=np.float32).reshape(16)
+    pos = vec3(cam_pos)
+    out = View()
+    check(lib().pyvr_cuda_view_from_matrices(f32_ptr(v), f32_ptr(p), f32_ptr(pos), _c.byref(out)))
+    return out
+
+
+def view_from_camera(camera, aspect: float) -> View:
+    position, _ = camera.get_camera_vectors()
+    return view_from_matrices(camera.get_view_matrix(), camera.get_projection_matrix(aspect), position)
+
+
+def compute_normals_host(volume: np.ndarray, device: int = 0, return_ms: bool = False):
+    """Host array in, host array out, through ``pyvr_cuda_compute_normals``."""
+    vol = np.ascontiguousarray(volume, dtype=np.float32)
+    out = np.empty(vol.shape + (3,), dtype=np.float32)
+    ms = _c.c_float(0.0)
+    check(lib().pyvr_cuda_compute_normals(device, vol.ctypes.data, out.ctypes.data,
+                                          vol.shape[0], vol.shape[1], vol.shape[2], 0, _c.byref(ms)))
+    return (out, ms.value) if return_ms else out
+
+
+class PinnedBuffer:
+    """Page-locked host memory exposed as a numpy ``uint8`` array (frame read-back target)."""
+
+    def __init__(self, nbytes: int):
+        self._ptr = _vp()
+        check(lib().pyvr_cuda_host_alloc(nbytes, _c.byref(self._ptr)))
+        self.nbytes = nbytes
+        self.array = np.ctypeslib.as_array((_c.c_uint8 * nbytes).from_address(self._ptr.value))
+
+    def close(self) -> None:
+        if self._ptr:
+            self.array = None
+            lib().pyvr_cuda_host_free(self._ptr)
+            self._ptr = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,273 @@
+"""``VolumeRenderer`` -- the drop-in for ``pyvr.moderngl_renderer.VolumeRenderer``.
+
+Same constructor, methods, defaults and error messages as the reference class
+(``pyvr/moderngl_renderer/renderer.py:19-320``); the OpenGL resource manager and the GLSL
+shader underneath are replaced by the sm_100a library behind ``include/pyvr_cuda.h``.
+``render()`` returns the same ``width*height*4`` RGBA8 bytes, bottom row first, holding the
+reference's blended ``(C*A, A*A)`` values.
+
+It accepts this package's host classes and, duck-typed, the reference's own ``pyvr`` objects, so a
+reference script switches backend by changing one import.  Extras that have no reference
+counterpart (``render_batch``, ``render_accum``, ``stats``) are additive.
+"""
+
+from __future__ import annotations
+
+import ctypes
+from typing import Iterable, Optional
+
+import numpy as np
+
+from ..camera import Camera
+from ..config import RenderConfig
+from ..lighting import Light
+from ..transferfunctions import build_rgba_lut
+from ..volume import Volume
+from . import _cabi
+
+# The shader's stop test is a literal (volume.frag.glsl:87); RenderConfig.opacity_threshold never
+# reaches it (renderer.py:303-309).
+REFERENCE_TERMINATION_ALPHA = 0.99
+
+
+def _is_a(obj, own_cls, name: str) -> bool:
+    """True for this package's class or the reference's class of the same name."""
+    if isinstance(obj, own_cls):
+        return True
+    t = type(obj)
+    return t.__name__ == name and t.__module__.split(".")[0] == "pyvr"
+
+
+class CudaVolumeRenderer:
+    def __init__(self, width=512, height=512, config=None, light=None, *, device: int = 0,
+                 texel_format: str = "f32", strict: bool = False,
+                 empty_space_skipping: bool = True, honor_config_termination: bool = False):
+        """
+        Args:
+            width, height, config, light: as the reference (balanced preset / ``Light.default()``).
+            device: CUDA device ordinal of this renderer's context.
+            texel_format: ``"f32"`` ({s,nx,ny,nz} binary32, parity configs) or ``"f16"``.
+            strict: reference-faithful arithmetic (slow; used to pin the kernel to the oracle).
+            empty_space_skipping: exact macrocell skipping (pixels unchanged).
+            honor_config_termination: NON-PARITY opt-in -- stop rays at
+                ``config.opacity_threshold`` (or never, if ``early_ray_termination`` is off)
+                instead of the shader's literal 0.99.
+        """
+        self.width = width
+        self.height = height
+        self.volume: Optional[Volume] = None
+        self.camera: Optional[Camera] = None
+
+        if config is None:
+            self.config = RenderConfig.balanced()
+        else:
+            if not _is_a(config, RenderConfig, "RenderConfig"):
+                raise TypeError(f"Expected RenderConfig instance, got {type(config)}")
+            self.config = config
+        if light is None:
+            self.light = Light.default()
+        else:
+            if not _is_a(light, Light, "Light"):
+                raise TypeError(f"Expected Light instance, got {type(light)}")
+            self.light = light
+
+        if texel_format not in ("f32", "f16"):
+            raise ValueError("texel_format must be 'f32' or 'f16'")
+        self.device = int(device)
+        self._texel_format = _cabi.TEXEL_F16X4 if texel_format == "f16" else _cabi.TEXEL_F32X4
+        self._strict = bool(strict)
+        self._ess = bool(empty_space_skipping)
+        self._honor_termination = bool(honor_config_termination)
+        self._lib = _cabi.lib()
+        self._ctx = ctypes.c_void_p()
+        _cabi.check(self._lib.pyvr_cuda_create(self.device, int(width), int(height), ctypes.byref(self._ctx)))
+        self._push_params()
+
+    # -- resource life cycle -------------------------------------------------------------
+    def close(self) -> None:
+        ctx, self._ctx = getattr(self, "_ctx", None), None
+        if ctx:
+            self._lib.pyvr_cuda_destroy(ctx)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- reference API ---------------------------------------------------------------------
+    def load_volume(self, volume: Volume) -> None:
+        if not _is_a(volume, Volume, "Volume"):
+            raise TypeError(
+                f"Expected Volume instance, got {type(volume)}. "
+                "Create a Volume instance: from pyvr.volume import Volume; "
+                "volume = Volume(data=your_array)")
+        data = volume.data
+        if data.ndim != 3:
+            raise ValueError("Volume data must be 3D")
+        data = np.ascontiguousarray(data, dtype=np.float32)  # manager.py:91-92 casts to float32
+        normals = None
+        if volume.has_normals:
+            if volume.normals.shape[-1] != 3:
+                raise ValueError("Normal volume must have 3 channels (last dimension).")
+            normals = np.ascontiguousarray(volume.normals, dtype=np.float32)
+        self.volume = volume
+        bmin, bmax = _cabi.vec3(volume.min_bounds), _cabi.vec3(volume.max_bounds)
+        _cabi.check(self._lib.pyvr_cuda_upload_volume(
+            self._ctx, data.ctypes.data, normals.ctypes.data if normals is not None else None,
+            data.shape[0], data.shape[1], data.shape[2], _cabi.f32_ptr(bmin), _cabi.f32_ptr(bmax),
+            self._texel_format, 0))
+
+    def set_camera(self, camera: Camera) -> None:
+        if not _is_a(camera, Camera, "Camera"):
+            raise TypeError(f"Expected Camera instance, got {type(camera)}")
+        self.camera = camera
+        aspect = self.width / self.height
+        view = np.ascontiguousarray(camera.get_view_matrix(), dtype=np.float32).reshape(16)
+        proj = np.ascontiguousarray(camera.get_projection_matrix(aspect), dtype=np.float32).reshape(16)
+        position, _ = camera.get_camera_vectors()
+        pos = _cabi.vec3(position)
+        _cabi.check(self._lib.pyvr_cuda_set_camera(
+            self._ctx, _cabi.f32_ptr(view), _cabi.f32_ptr(proj), _cabi.f32_ptr(pos)))
+
+    def set_light(self, light: Light) -> None:
+        if not _is_a(light, Light, "Light"):
+            raise TypeError(f"Expected Light instance, got {type(light)}")
+        self.light = light
+        self._push_params()
+
+    def set_transfer_functions(self, color_transfer_function, opacity_transfer_function,
+                               size: Optional[int] = None) -> None:
+        lut = np.ascontiguousarray(
+            build_rgba_lut(color_transfer_function, opacity_transfer_function, size), dtype=np.float32)
+        _cabi.check(self._lib.pyvr_cuda_set_lut(self._ctx, lut.ctypes.data, lut.shape[0]))
+
+    def render(self) -> bytes:
+        """Raw RGBA8 pixels, ``width*height*4`` bytes, bottom row first."""
+        out = np.empty(self.width * self.height * 4, dtype=np.uint8)
+        _cabi.check(self._lib.pyvr_cuda_render(self._ctx, out.ctypes.data, 0))
+        return out.tobytes()
+
+    def render_to_pil(self, data=None):
+        from PIL import Image
+
+        if data is None:
+            data = self.render()
+        image = Image.frombytes("RGBA", (self.width, self.height), data)
+        return image.transpose(Image.FLIP_TOP_BOTTOM)
+
+    def set_config(self, config) -> None:
+        if not _is_a(config, RenderConfig, "RenderConfig"):
+            raise TypeError(f"Expected RenderConfig instance, got {type(config)}")
+        self.config = config
+        self._push_params()
+
+    def get_config(self):
+        return self.config
+
+    def get_light(self):
+        return self.light
+
+    def get_volume(self) -> Optional[Volume]:
+        return self.volume
+
+    def get_camera(self) -> Optional[Camera]:
+        return self.camera
+
+    # -- additive API ----------------------------------------------------------------------
+    def set_lut(self, rgba: np.ndarray) -> None:
+        """Upload a ready ``(size, 4) float32`` RGBA table."""
+        lut = np.ascontiguousarray(rgba, dtype=np.float32)
+        if lut.ndim != 2 or lut.shape[1] != 4:
+            raise ValueError("LUT must have shape (size, 4)")
+        _cabi.check(self._lib.pyvr_cuda_set_lut(self._ctx, lut.ctypes.data, lut.shape[0]))
+
+    def render_array(self, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """``render()`` into a ``(height, width, 4) uint8`` array (pinned or not); no ``bytes`` copy."""
+        if out is None:
+            out = np.empty((self.height, self.width, 4), dtype=np.uint8)
+        _cabi.check(self._lib.pyvr_cuda_render(self._ctx, out.ctypes.data, 0))
+        return out
+
+    def make_views(self, cameras: Iterable) -> ctypes.Array:
+        aspect = self.width / self.height
+        cams = list(cameras)
+        views = (_cabi.View * len(cams))()
+        for i, cam in enumerate(cams):
+            views[i] = _cabi.view_from_camera(cam, aspect)
+        return views
+
+    def render_batch(self, cameras=None, *, views=None, out: Optional[np.ndarray] = None,
+                     device_ptr: Optional[int] = None) -> Optional[np.ndarray]:
+        """Render many views in one call (the turntable path).
+
+        ``out``: ``(n, height, width, 4) uint8`` host array (pinned for full PCIe rate); allocated if
+        omitted.  ``device_ptr``: raw device pointer to receive the frames instead (nothing returned).
+        Frame k's device->host copy overlaps the march of frame k+1.
+        """
+        if views is None:
+            views = self.make_views(cameras)
+        n = len(views)
+        if device_ptr is not None:
+            _cabi.check(self._lib.pyvr_cuda_render_batch(self._ctx, views, n, ctypes.c_void_p(device_ptr), 1))
+            return None
+        if out is None:
+            out = np.empty((n, self.height, self.width, 4), dtype=np.uint8)
+        if out.nbytes < n * self.height * self.width * 4 or not out.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous buffer of n*height*width*4 bytes")
+        _cabi.check(self._lib.pyvr_cuda_render_batch(self._ctx, views, n, out.ctypes.data, 0))
+        return out
+
+    def render_accum(self) -> np.ndarray:
+        """Fragment colour before blending: ``(height, width, 4) float32`` = (acc_rgb, acc_a)."""
+        out = np.empty((self.height, self.width, 4), dtype=np.float32)
+        _cabi.check(self._lib.pyvr_cuda_render_accum(self._ctx, out.ctypes.data, 0))
+        return out
+
+    def set_stream(self, cuda_stream: int) -> None:
+        """Run this renderer's work on an existing ``cudaStream_t`` (e.g. torch's current stream)."""
+        _cabi.check(self._lib.pyvr_cuda_set_stream(self._ctx, ctypes.c_void_p(cuda_stream)))
+
+    @property
+    def stats(self) -> dict:
+        """Work counters and device time of the last render call (``pyvr_stats``)."""
+        s = _cabi.Stats()
+        _cabi.check(self._lib.pyvr_cuda_get_stats(self._ctx, ctypes.byref(s)))
+        return s.as_dict()
+
+    # -- internals -------------------------------------------------------------------------
+    def _termination_alpha(self) -> float:
+        if not self._honor_termination:
+            return REFERENCE_TERMINATION_ALPHA
+        if not self.config.early_ray_termination:
+            return 2.0  # never reached
+        return float(self.config.opacity_threshold)
+
+    def _push_params(self) -> None:
+        """``_update_render_config`` + ``_update_light`` of the reference (renderer.py:303-316)."""
+        p = _cabi.Params()
+        p.step_size = float(self.config.step_size)
+        p.max_steps = int(self.config.max_steps)
+        p.reference_step_size = float(self.config.reference_step_size)
+        p.ambient = float(self.light.ambient_intensity)
+        p.diffuse = float(self.light.diffuse_intensity)
+        p.light_position[:] = [float(v) for v in _cabi.vec3(self.light.position)]
+        p.light_target[:] = [float(v) for v in _cabi.vec3(self.light.target)]
+        p.termination_alpha = self._termination_alpha()
+        flags = 0
+        if self._strict:
+            flags |= _cabi.FLAG_STRICT
+        elif self._ess:
+            flags |= _cabi.FLAG_ESS
+        p.flags = flags
+        _cabi.check(self._lib.pyvr_cuda_set_params(self._ctx, ctypes.byref(p)))
+
+
+# Same alias the reference exports (renderer.py:320).
+VolumeRenderer = CudaVolumeRenderer

@@ -1,0 +1,62 @@
+"""K2 (compute_normal_volume on the GPU) vs the reference's numpy output (golden) and the oracle.
+
+Bar: abs(delta) <= 1e-5 * max(1, abs(ref)) per component (BASELINE.json); in practice bit-exact,
+which is asserted too because the kernel performs the same binary32 operations in the same order."""
+
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from pyvr_b200 import Volume, compute_normal_volume, create_sample_volume
+from pyvr_b200.cuda_renderer import _cabi
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(got, want, name):
+    assert got.dtype == np.float32 and got.shape == want.shape, name
+    tol = 1e-5 * np.maximum(1.0, np.abs(want))
+    assert np.all(np.abs(got - want) <= tol), name
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), f"{name}: not bit-exact"
+
+
+def test_golden_cases(golden_dir):
+    z = np.load(os.path.join(golden_dir, "normals.npz"))
+    for key in [k[:-4] for k in z.files if k.endswith("__in")]:
+        _check(compute_normal_volume(z[key + "__in"]), z[key + "__out"], key)
+
+
+def test_double_sphere_128_hash(golden_dir):
+    meta = json.load(open(os.path.join(golden_dir, "meta.json")))
+    got = compute_normal_volume(create_sample_volume(128, "double_sphere"))
+    assert hashlib.sha256(got.tobytes()).hexdigest() == meta["normal_volume_sha256"]["double_sphere_128"]
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 1), (1, 5, 8), (7, 1, 4), (3, 3, 3), (5, 6, 7), (16, 12, 20),
+                                   (33, 17, 64), (64, 64, 64), (2, 2, 4)])
+def test_ragged_and_vector_paths_vs_oracle(shape):
+    rng = np.random.default_rng(sum(shape))
+    vol = (rng.standard_normal(shape) * 3).astype(np.float32)
+    _check(compute_normal_volume(vol), oracle.normals(vol), str(shape))
+
+
+def test_large_volume_vs_oracle_and_timing():
+    vol = create_sample_volume(256, "helix")
+    got, ms = _cabi.compute_normals_host(vol, return_ms=True)
+    _check(got, oracle.normals(vol), "helix_256")
+    assert 0 < ms < 50
+
+
+def test_volume_compute_normals_method_and_dtype_cast():
+    v = Volume(data=create_sample_volume(24, "torus").astype(np.float64))
+    v.compute_normals()
+    assert v.normals.shape == (24, 24, 24, 3) and v.normals.dtype == np.float32
+    _check(v.normals, oracle.normals(v.data.astype(np.float32)), "torus_24")
+    with pytest.raises(ValueError, match="Unsupported method"):
+        v.compute_normals("sobel")
+    with pytest.raises(ValueError, match="must be 3D"):
+        compute_normal_volume(np.zeros((4, 4), np.float32))
