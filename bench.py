@@ -24,6 +24,7 @@ driver, which do not exist in this image ("kind": "port").
 from __future__ import annotations
 
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -349,7 +350,7 @@ def main():
             "frames_per_s": frames / (ms * 1e-3),
             "samples_per_frame": all_samples / frames,
             "e2e": {"value": e2e_value, "unit": "Gsamples/s", "frames_per_s": frames / (e2e_ms * 1e-3),
-                    "h2d_bytes_per_step": per_step * 48, "d2h_bytes_per_step": per_step * frame_bytes,
+                    "h2d_bytes_per_step": per_step * ctypes.sizeof(_cabi.View), "d2h_bytes_per_step": per_step * frame_bytes,
                     "api": "VolumeRenderer.render_batch(views, out=pinned host buffer)", "frame_checksum": checksum},
             "gpu_launches": int(launches),
             "roofline": {

@@ -50,17 +50,23 @@ typedef enum {
 typedef struct pyvr_ctx pyvr_ctx;
 
 /*
- * Ray basis of one view: for pixel centre (px+0.5, py+0.5), ndc = 2*(p/size) - 1 and
- *   dir = normalize(u * ndc.x + v * ndc.y + w),  origin = camera position.
- * This is the closed form of ray_direction() (volume.frag.glsl:47-54) for ANY view/projection
- * matrices: inverse(P) and inverse(V) are applied once on the host instead of per fragment.
- * py = 0 is the BOTTOM row, as in the GL framebuffer the reference reads back.
+ * One view.  The march derives the ray of pixel centre (px+0.5, py+0.5), ndc = 2*(p/size) - 1, exactly
+ * as ray_direction() does (volume.frag.glsl:47-54) when has_matrices != 0:
+ *   eye = inv_proj * (ndc, -1, 1); eye.zw = (-1, 0); dir = normalize((inv_view * eye).xyz)
+ * with inv_proj / inv_view = inverse(projection_matrix) / inverse(view_matrix) evaluated once on the
+ * host in binary32 (the shader re-evaluates them per fragment).  With has_matrices == 0 the closed form
+ *   dir = normalize(u * ndc.x + v * ndc.y + w)
+ * is used instead (u, v, w derived in binary64; differs from the matrix path by ~1e-7 relative).
+ * origin = camera_pos.  py = 0 is the BOTTOM row, as in the GL framebuffer the reference reads back.
  */
 typedef struct {
     float origin[3];
     float u[3];
     float v[3];
     float w[3];
+    float inv_proj[16];      /* column-major, as GL holds the uniform */
+    float inv_view[16];
+    int32_t has_matrices;
 } pyvr_view;
 
 /* Uniforms of the shader other than camera and bounds (volume.frag.glsl:10-19). */

@@ -75,8 +75,6 @@ struct pyvr_ctx {
     pyvr_view view{};
     pyvr_params params{};
     bool have_view = false;
-    bool have_matrices = false;    // set_camera keeps binary32 inverses for the STRICT path
-    float inv_proj[16] = {}, inv_view[16] = {};
 
     // frame resources
     pyvr_view *d_views = nullptr;
@@ -125,7 +123,7 @@ bool invert4(const double m[4][4], double out[4][4]) {
 }
 
 // GLSL inverse(mat4) evaluated in binary32 by cofactor expansion (column-major m[c*4+r]); the STRICT
-// kernel applies the result per pixel.  Same expression order as the oracle's restatement, so both
+// march applies the result per pixel.  Same expression order as the oracle's restatement, so both
 // sides round identically ("Arithmetic contract").
 void inverse4_f32(const float *m, float *o) {
     const float a00 = m[0], a01 = m[1], a02 = m[2], a03 = m[3], a10 = m[4], a11 = m[5], a12 = m[6], a13 = m[7];
@@ -240,9 +238,6 @@ MarchArgs make_args(const pyvr_ctx *c) {
     a.term_alpha = p.termination_alpha;
     a.flags = p.flags;
     a.counters = c->d_counters;
-    a.use_matrices = c->have_matrices ? 1 : 0;
-    memcpy(a.inv_proj, c->inv_proj, sizeof a.inv_proj);
-    memcpy(a.inv_view, c->inv_view, sizeof a.inv_view);
     return a;
 }
 
@@ -464,6 +459,9 @@ int pyvr_cuda_view_from_matrices(const float view[16], const float proj[16], con
         out->w[r] = (float)(iV[r][0] * ex_c + iV[r][1] * ey_c - iV[r][2]);
         out->origin[r] = cam_pos[r];
     }
+    inverse4_f32(proj, out->inv_proj);
+    inverse4_f32(view, out->inv_view);
+    out->has_matrices = 1;
     return PYVR_OK;
 }
 
@@ -474,9 +472,6 @@ int pyvr_cuda_set_camera(pyvr_ctx *c, const float view[16], const float proj[16]
     if (rc != PYVR_OK) return rc;
     c->view = v;
     c->have_view = true;
-    inverse4_f32(proj, c->inv_proj);
-    inverse4_f32(view, c->inv_view);
-    c->have_matrices = true;
     return PYVR_OK;
 }
 
@@ -484,7 +479,6 @@ int pyvr_cuda_set_view(pyvr_ctx *c, const pyvr_view *view) {
     if (!c || !view) return fail(PYVR_ERR_INVALID, "NULL argument");
     c->view = *view;
     c->have_view = true;
-    c->have_matrices = false;
     return PYVR_OK;
 }
 

@@ -41,10 +41,6 @@ struct VolumeDesc {
 struct MarchArgs {
     VolumeDesc vol;
     const pyvr_view *views;        // device array, indexed by blockIdx.z
-    // STRICT path only: inverse(projection_matrix), inverse(view_matrix) in binary32, column-major,
-    // applied per pixel exactly as ray_direction() does (volume.frag.glsl:47-54)
-    float inv_proj[16], inv_view[16];
-    int use_matrices;
     const float4 *lut;             // device, lut_size entries
     int lut_size;
     int width, height;

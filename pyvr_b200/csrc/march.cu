@@ -151,7 +151,7 @@ march_kernel(const __grid_constant__ MarchArgs a) {
     const int px = blockIdx.x * TILE_W + (warp & 1) * 8 + (lane & 7);
     const int py = blockIdx.y * TILE_H + (warp >> 1) * 4 + (lane >> 3);
     const bool in_image = px < a.width && py < a.height;
-    const pyvr_view vw = a.views[blockIdx.z];
+    const pyvr_view &vw = a.views[blockIdx.z];
     const VolumeDesc &vol = a.vol;
 
     Accum acc = {0.0f, 0.0f, 0.0f, 0.0f};
@@ -159,13 +159,16 @@ march_kernel(const __grid_constant__ MarchArgs a) {
     bool hit = false, terminated = false;
 
     if (in_image && vol.texels != nullptr && a.lut_size > 0) {
-        // volume.vert.glsl:8 at the pixel centre, volume.frag.glsl:33-35,47-54 in closed form
+        // ---- ray set-up: the oracle's arithmetic in BOTH modes.  The first sample sits exactly on the
+        // box surface, so whether it passes the validity test is decided by the last bit of these
+        // operations; any shortcut here would flip that coin for volumes that are opaque at the faces.
+        // volume.vert.glsl:8 at the pixel centre, volume.frag.glsl:33-35,47-54
         const float ndx = ((float)px + 0.5f) / (float)a.width * 2.0f - 1.0f;
         const float ndy = ((float)py + 0.5f) / (float)a.height * 2.0f - 1.0f;
         float dx, dy, dz;
-        if (STRICT && a.use_matrices) {
+        if (vw.has_matrices) {
             // eye = inverse(P) * (ndc, -1, 1); eye.zw = (-1, 0); world = inverse(V) * eye
-            const float *ip = a.inv_proj, *iv = a.inv_view;
+            const float *ip = vw.inv_proj, *iv = vw.inv_view;
             const float ex = ip[0] * ndx + ip[4] * ndy + ip[8] * -1.0f + ip[12] * 1.0f;
             const float ey = ip[1] * ndx + ip[5] * ndy + ip[9] * -1.0f + ip[13] * 1.0f;
             dx = iv[0] * ex + iv[4] * ey + iv[8] * -1.0f + iv[12] * 0.0f;
@@ -216,7 +219,12 @@ march_kernel(const __grid_constant__ MarchArgs a) {
                 }
                 terminated = (i < n_steps) || (n_steps < a.max_steps && acc.a >= a.term_alpha);
             } else {
-                // voxel-space lattice: x(i) = X0 + i*DX, valid iff -0.5 <= x <= n-0.5 on every axis
+                // voxel-space lattice: x(i) = X0 + i*DX, valid iff -0.5 <= x <= n-0.5 on every axis;
+                // sample 0 (on the box surface) takes the reference's own validity test instead.
+                const float t0x = (p0x - vol.bmin[0]) / (vol.bmax[0] - vol.bmin[0]);
+                const float t0y = (p0y - vol.bmin[1]) / (vol.bmax[1] - vol.bmin[1]);
+                const float t0z = (p0z - vol.bmin[2]) / (vol.bmax[2] - vol.bmin[2]);
+                const bool valid0 = t0x >= 0.0f && t0x <= 1.0f && t0y >= 0.0f && t0y <= 1.0f && t0z >= 0.0f && t0z <= 1.0f;
                 const float X0 = fmaf(p0x, vol.vscale[0], vol.voff[0]), DX = sx * vol.vscale[0];
                 const float Y0 = fmaf(p0y, vol.vscale[1], vol.voff[1]), DY = sy * vol.vscale[1];
                 const float Z0 = fmaf(p0z, vol.vscale[2], vol.voff[2]), DZ = sz * vol.vscale[2];
@@ -226,8 +234,13 @@ march_kernel(const __grid_constant__ MarchArgs a) {
                 int i = 0;
                 while (i < n_steps) {
                     const float fi = (float)i;
-                    const float x = fmaf(fi, DX, X0), y = fmaf(fi, DY, Y0), z = fmaf(fi, DZ, Z0);
-                    if (x >= -0.5f && x <= hx && y >= -0.5f && y <= hy && z >= -0.5f && z <= hz) {
+                    float x = fmaf(fi, DX, X0), y = fmaf(fi, DY, Y0), z = fmaf(fi, DZ, Z0);
+                    bool valid = x >= -0.5f && x <= hx && y >= -0.5f && y <= hy && z >= -0.5f && z <= hz;
+                    if (i == 0) {
+                        valid = valid0;
+                        x = fminf(fmaxf(x, -0.5f), hx); y = fminf(fmaxf(y, -0.5f), hy); z = fminf(fmaxf(z, -0.5f), hz);
+                    }
+                    if (valid) {
                         const Taps tx = voxel_taps(x, vol.n[0]), ty = voxel_taps(y, vol.n[1]),
                                    tz = voxel_taps(z, vol.n[2]);
                         if (ess) {
@@ -235,13 +248,13 @@ march_kernel(const __grid_constant__ MarchArgs a) {
                             const uint8_t active =
                                 __ldg(vol.cell_active + ((size_t)cx * vol.ncell[1] + cy) * vol.ncell[2] + cz);
                             if (!active) {
-                                // whole steps that stay inside this cell on every axis (conservative by 0.01 step)
-                                const float ex = ((DX > 0.0f ? (float)(8 * cx + 8) : (float)(8 * cx)) - x) * rDX;
-                                const float ey = ((DY > 0.0f ? (float)(8 * cy + 8) : (float)(8 * cy)) - y) * rDY;
-                                const float ez = ((DZ > 0.0f ? (float)(8 * cz + 8) : (float)(8 * cz)) - z) * rDZ;
-                                // a zero direction component gives +-inf or NaN: fminf ignores NaN, inf never wins
-                                float tmin = fminf(fminf(DX != 0.0f ? ex : 3.0e38f, DY != 0.0f ? ey : 3.0e38f),
-                                                   DZ != 0.0f ? ez : 3.0e38f);
+                                // Whole steps that stay inside this cell (and inside the volume) on every
+                                // axis, conservative by 0.01 step.  A zero direction component never exits.
+                                const float ex = ((DX > 0.0f ? fminf((float)(8 * cx + 8), hx) : fmaxf((float)(8 * cx), -0.5f)) - x) * rDX;
+                                const float ey = ((DY > 0.0f ? fminf((float)(8 * cy + 8), hy) : fmaxf((float)(8 * cy), -0.5f)) - y) * rDY;
+                                const float ez = ((DZ > 0.0f ? fminf((float)(8 * cz + 8), hz) : fmaxf((float)(8 * cz), -0.5f)) - z) * rDZ;
+                                const float tmin = fminf(fminf(DX != 0.0f ? ex : 3.0e38f, DY != 0.0f ? ey : 3.0e38f),
+                                                         DZ != 0.0f ? ez : 3.0e38f);
                                 int skip = (int)fminf(floorf(tmin - 0.01f), (float)(n_steps - i));
                                 skip = max(skip, 1);
                                 n_samples += skip;

@@ -87,9 +87,11 @@ cell_minmax_kernel(VolumeDesc v, float2 *__restrict__ out) {
     }
 }
 
-// LUT taps a density can select: x = d*size - 0.5, taps floor(x), floor(x)+1, both clamped.  The cell
-// is inactive iff every LUT alpha in the tap range of [lo, hi], widened by one entry on each side
-// for binary32 slop in the trilinear filter, is exactly zero.
+// LUT taps a density can select (march.cu axis_taps): x = d*size - 0.5, taps clamp(floor(x)) and
+// clamp(floor(x)+1).  Every sample of the cell has lo <= d <= hi up to a few ulps of lerp round-off,
+// so [lo, hi] is widened by 1e-6 relative (~8 ulp) and x is evaluated with the very expression the
+// march uses: binary32 multiply/subtract are monotonic, hence floor(x(d)) lies between the two ends.
+// The cell is inactive iff every LUT alpha in that tap range is exactly zero.
 __global__ void __launch_bounds__(256)
 cell_classify_kernel(const float2 *__restrict__ mm, size_t n_cells, const float4 *__restrict__ lut,
                      int lut_size, uint8_t *__restrict__ active) {
@@ -106,9 +108,11 @@ cell_classify_kernel(const float2 *__restrict__ mm, size_t n_cells, const float4
     for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_cells;
          c += (size_t)gridDim.x * blockDim.x) {
         const float2 r = mm[c];
+        const float slack = fmaxf(fabsf(r.x), fabsf(r.y)) * 1e-6f + 1e-30f;
+        const float lo = r.x - slack, hi = r.y + slack;
         const float size = (float)lut_size;
-        float xl = floorf(r.x * size - 0.5f) - 1.0f, xh = floorf(r.y * size - 0.5f) + 2.0f;
-        const int jl = (int)fminf(fmaxf(xl, 0.0f), size - 1.0f);
+        const float xl = floorf(lo * size - 0.5f), xh = floorf(hi * size - 0.5f) + 1.0f;
+        const int jl = (int)fminf(fmaxf(xl, 0.0f), size - 1.0f);   // NaN/-inf -> 0, +inf -> size-1
         const int jh = (int)fminf(fmaxf(xh, 0.0f), size - 1.0f);
         active[c] = (s_nonzero_before[jh + 1] - s_nonzero_before[jl]) != 0 ? 1 : 0;
     }

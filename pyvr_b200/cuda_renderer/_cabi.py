@@ -26,8 +26,9 @@ _vp, _i, _fp = _c.c_void_p, _c.c_int, _c.POINTER(_c.c_float)
 
 
 class View(ctypes.Structure):
-    """``pyvr_view``: ray origin and the basis of ``dir = normalize(u*ndc.x + v*ndc.y + w)``."""
-    _fields_ = [("origin", _c.c_float * 3), ("u", _c.c_float * 3), ("v", _c.c_float * 3), ("w", _c.c_float * 3)]
+    """``pyvr_view``: ray origin, closed-form basis and the binary32 inverse matrices of one view."""
+    _fields_ = [("origin", _c.c_float * 3), ("u", _c.c_float * 3), ("v", _c.c_float * 3), ("w", _c.c_float * 3),
+                ("inv_proj", _c.c_float * 16), ("inv_view", _c.c_float * 16), ("has_matrices", _c.c_int32)]
 
 
 class Params(ctypes.Structure):
