@@ -65,7 +65,7 @@ struct pyvr_ctx {
     float2 *cell_minmax = nullptr;
     uint8_t *cell_active = nullptr;
     size_t n_cells = 0;
-    int layout = 1;  // 0 linear, 1 8^3 bricks
+    int layout = 2;  // bit 0: 8x8 bricks of lines (else plain rows); bit 1: slot swizzle
 
     // transfer function
     float4 *lut = nullptr;
@@ -164,22 +164,30 @@ void fill_volume_desc(pyvr_ctx *c, int shape0, int shape1, int shape2, const flo
         v.voff[a] = (float)(-(double)bmin[a] * (double)v.n[a] / ext - 0.5);
         v.ncell[a] = (v.n[a] + 7) / 8;
     }
-    if (c->layout == 1) {
-        const long long nby = v.ncell[1], nbz = v.ncell[2];
-        v.map[0] = {3, 7, nby * nbz * 512, 64};
-        v.map[1] = {3, 7, nbz * 512, 8};
-        v.map[2] = {3, 7, 512, 1};
-    } else {
-        v.map[0] = {31, 0x7fffffff, 0, (long long)v.n[1] * v.n[2]};
-        v.map[1] = {31, 0x7fffffff, 0, (long long)v.n[2]};
-        v.map[2] = {31, 0x7fffffff, 0, 1};
+    // lines of SLOTS consecutive-z texels; see common.cuh
+    v.slot_shift = c->half_texels ? 4 : 3;
+    const long long nzl = (v.n[2] + (1 << v.slot_shift) - 1) >> v.slot_shift;   // lines per z-row
+    if (c->layout & 1) {      // 8x8 bricks of lines
+        const long long nby = v.ncell[1];
+        v.map[0] = {3, 7, nby * nzl * 64, 8};
+        v.map[1] = {3, 7, nzl * 64, 1};
+        v.map[2] = {v.slot_shift, 0, 64, 0};
+    } else {                  // plain rows
+        v.map[0] = {31, 0x7fffffff, 0, (long long)v.n[1] * nzl};
+        v.map[1] = {31, 0x7fffffff, 0, nzl};
+        v.map[2] = {v.slot_shift, 0, 1, 0};
     }
+    const bool swizzle = (c->layout & 2) != 0;
+    v.swz[0] = swizzle ? 1 : 0;
+    v.swz[1] = swizzle ? 3 : 0;
 }
 
 size_t texel_count(const pyvr_ctx *c) {
     const VolumeDesc &v = c->vol;
-    if (c->layout == 1) return (size_t)v.ncell[0] * v.ncell[1] * v.ncell[2] * 512;
-    return (size_t)v.n[0] * v.n[1] * v.n[2];
+    const size_t slots = (size_t)1 << v.slot_shift;
+    const size_t nzl = ((size_t)v.n[2] + slots - 1) >> v.slot_shift;
+    if (c->layout & 1) return (size_t)v.ncell[0] * v.ncell[1] * 64 * nzl * slots;
+    return (size_t)v.n[0] * v.n[1] * nzl * slots;
 }
 
 int classify_cells(pyvr_ctx *c) {
@@ -248,7 +256,7 @@ int march(pyvr_ctx *c, int first, int n, uchar4 *out8, float4 *out_acc, size_t e
     a.out8 = out8;
     a.out_acc = out_acc;
     CU(cudaEventRecord(c->ev[2 * ev_pair], c->stream));
-    CU(launch_march(a, n, c->half_texels, c->stream));
+    CU(launch_march(a, n, c->half_texels, c->texel_bytes / (c->half_texels ? 8 : 16) >= ((size_t)1 << 31), c->stream));
     CU(cudaEventRecord(c->ev[2 * ev_pair + 1], c->stream));
     return PYVR_OK;
 }
@@ -303,7 +311,12 @@ int pyvr_cuda_create(int device, int width, int height, pyvr_ctx **out_ctx) {
     c->width = width;
     c->height = height;
     const char *layout = getenv("PYVR_CUDA_LAYOUT");
-    if (layout) c->layout = strcmp(layout, "linear") == 0 ? 0 : 1;
+    if (layout) {
+        if (strcmp(layout, "linear") == 0) c->layout = 0;
+        else if (strcmp(layout, "brick") == 0) c->layout = 1;
+        else if (strcmp(layout, "linear_swz") == 0) c->layout = 2;
+        else if (strcmp(layout, "brick_swz") == 0) c->layout = 3;
+    }
     // defaults of the reference renderer: balanced preset, Light.default(), bounds +-0.5
     c->params.step_size = 0.01f; c->params.max_steps = 500; c->params.reference_step_size = 0.01f;
     c->params.ambient = 0.2f; c->params.diffuse = 0.8f;
@@ -361,7 +374,7 @@ int pyvr_cuda_set_stream(pyvr_ctx *c, void *cuda_stream) {
 int pyvr_cuda_set_option(pyvr_ctx *c, const char *key, int value) {
     if (!c || !key) return fail(PYVR_ERR_INVALID, "ctx or key is NULL");
     if (strcmp(key, "layout") == 0) {
-        if (value != 0 && value != 1) return fail(PYVR_ERR_INVALID, "layout must be 0 (linear) or 1 (bricks)");
+        if (value < 0 || value > 3) return fail(PYVR_ERR_INVALID, "layout must be 0..3 (bit 0 bricks, bit 1 swizzle)");
         if (c->have_volume && value != c->layout)
             return fail(PYVR_ERR_STATE, "layout must be chosen before the volume is uploaded");
         c->layout = value;

@@ -51,14 +51,10 @@ __device__ __forceinline__ Taps voxel_taps(float x, int n) {
     return t;
 }
 
-__device__ __forceinline__ long long axis_offset(const AxisMap &m, int i) {
-    return (long long)(i >> m.shift) * m.outer + (long long)(i & m.mask) * m.inner;
-}
-
 __device__ __forceinline__ float lerpf(float a, float b, float t) { return fmaf(t, b - a, a); }
 
-template <bool HALF>
-__device__ __forceinline__ float4 load_texel(const void *base, long long idx) {
+template <bool HALF, typename IDX>
+__device__ __forceinline__ float4 load_texel(const void *base, IDX idx) {
     if constexpr (HALF) {
         uint2 raw = __ldg(reinterpret_cast<const uint2 *>(base) + idx);
         __half2 a = *reinterpret_cast<__half2 *>(&raw.x), b = *reinterpret_cast<__half2 *>(&raw.y);
@@ -73,21 +69,27 @@ struct Corner8 {
     float4 c[8];  // index = (x_tap << 2) | (y_tap << 1) | z_tap
 };
 
-template <bool HALF>
+// Eight corner fetches.  IDX is int (packed array < 2^31 texels) or long long.
+template <bool HALF, typename IDX>
 __device__ __forceinline__ Corner8 gather(const VolumeDesc &v, const Taps &tx, const Taps &ty, const Taps &tz) {
-    long long ox0 = axis_offset(v.map[0], tx.i0), ox1 = axis_offset(v.map[0], tx.i1);
-    long long oy0 = axis_offset(v.map[1], ty.i0), oy1 = axis_offset(v.map[1], ty.i1);
-    long long oz0 = axis_offset(v.map[2], tz.i0), oz1 = axis_offset(v.map[2], tz.i1);
-    long long b00 = ox0 + oy0, b01 = ox0 + oy1, b10 = ox1 + oy0, b11 = ox1 + oy1;
+    constexpr int LS = HALF ? 4 : 3, SLOT_MASK = (1 << LS) - 1;
+    const IDX ox0 = (IDX)axis_offset(v.map[0], tx.i0), ox1 = (IDX)axis_offset(v.map[0], tx.i1);
+    const IDX oy0 = (IDX)axis_offset(v.map[1], ty.i0), oy1 = (IDX)axis_offset(v.map[1], ty.i1);
+    const IDX oz0 = (IDX)axis_offset(v.map[2], tz.i0), oz1 = (IDX)axis_offset(v.map[2], tz.i1);
+    const int sx0 = v.swz[0] * tx.i0, sx1 = v.swz[0] * tx.i1, sy0 = v.swz[1] * ty.i0, sy1 = v.swz[1] * ty.i1;
+    const IDX l00 = ox0 + oy0, l01 = ox0 + oy1, l10 = ox1 + oy0, l11 = ox1 + oy1;
+    const int s00 = sx0 + sy0, s01 = sx0 + sy1, s10 = sx1 + sy0, s11 = sx1 + sy1;
+#define PYVR_AT(l, s, oz, iz) ((((l) + (oz)) << LS) + (IDX)(((s) + (iz)) & SLOT_MASK))
     Corner8 r;
-    r.c[0] = load_texel<HALF>(v.texels, b00 + oz0);
-    r.c[1] = load_texel<HALF>(v.texels, b00 + oz1);
-    r.c[2] = load_texel<HALF>(v.texels, b01 + oz0);
-    r.c[3] = load_texel<HALF>(v.texels, b01 + oz1);
-    r.c[4] = load_texel<HALF>(v.texels, b10 + oz0);
-    r.c[5] = load_texel<HALF>(v.texels, b10 + oz1);
-    r.c[6] = load_texel<HALF>(v.texels, b11 + oz0);
-    r.c[7] = load_texel<HALF>(v.texels, b11 + oz1);
+    r.c[0] = load_texel<HALF, IDX>(v.texels, PYVR_AT(l00, s00, oz0, tz.i0));
+    r.c[1] = load_texel<HALF, IDX>(v.texels, PYVR_AT(l00, s00, oz1, tz.i1));
+    r.c[2] = load_texel<HALF, IDX>(v.texels, PYVR_AT(l01, s01, oz0, tz.i0));
+    r.c[3] = load_texel<HALF, IDX>(v.texels, PYVR_AT(l01, s01, oz1, tz.i1));
+    r.c[4] = load_texel<HALF, IDX>(v.texels, PYVR_AT(l10, s10, oz0, tz.i0));
+    r.c[5] = load_texel<HALF, IDX>(v.texels, PYVR_AT(l10, s10, oz1, tz.i1));
+    r.c[6] = load_texel<HALF, IDX>(v.texels, PYVR_AT(l11, s11, oz0, tz.i0));
+    r.c[7] = load_texel<HALF, IDX>(v.texels, PYVR_AT(l11, s11, oz1, tz.i1));
+#undef PYVR_AT
     return r;
 }
 
@@ -140,7 +142,7 @@ __device__ __forceinline__ void shade(const MarchArgs &a, const float4 *s_lut, c
     acc.a = fmaf(t, alpha, acc.a);
 }
 
-template <bool STRICT, bool HALF>
+template <bool STRICT, bool HALF, typename IDX>
 __global__ void __launch_bounds__(CTA_THREADS)
 march_kernel(const __grid_constant__ MarchArgs a) {
     extern __shared__ float4 s_lut[];
@@ -212,7 +214,7 @@ march_kernel(const __grid_constant__ MarchArgs a) {
                         ++n_samples; ++n_fetched;
                         const Taps tx = axis_taps(tcx, vol.n[0]), ty = axis_taps(tcy, vol.n[1]),
                                    tz = axis_taps(tcz, vol.n[2]);
-                        const Corner8 k = gather<HALF>(vol, tx, ty, tz);
+                        const Corner8 k = gather<HALF, IDX>(vol, tx, ty, tz);
                         shade<true>(a, s_lut, k, tx.f, ty.f, tz.f, acc);
                     }
                     pxw += sx; pyw += sy; pzw += sz;
@@ -263,7 +265,7 @@ march_kernel(const __grid_constant__ MarchArgs a) {
                             }
                         }
                         ++n_samples; ++n_fetched;
-                        const Corner8 k = gather<HALF>(vol, tx, ty, tz);
+                        const Corner8 k = gather<HALF, IDX>(vol, tx, ty, tz);
                         shade<false>(a, s_lut, k, tx.f, ty.f, tz.f, acc);
                         if (acc.a >= a.term_alpha) { terminated = true; break; }
                     }
@@ -309,10 +311,10 @@ march_kernel(const __grid_constant__ MarchArgs a) {
     }
 }
 
-template <bool STRICT, bool HALF>
+template <bool STRICT, bool HALF, typename IDX>
 cudaError_t launch_one(const MarchArgs &a, int n_views, cudaStream_t stream) {
     const size_t smem = (size_t)a.lut_size * sizeof(float4);
-    auto kern = march_kernel<STRICT, HALF>;
+    auto kern = march_kernel<STRICT, HALF, IDX>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -322,12 +324,20 @@ cudaError_t launch_one(const MarchArgs &a, int n_views, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
+template <bool STRICT, bool HALF>
+cudaError_t launch_idx(const MarchArgs &a, int n_views, bool wide, cudaStream_t stream) {
+    return wide ? launch_one<STRICT, HALF, long long>(a, n_views, stream)
+                : launch_one<STRICT, HALF, int>(a, n_views, stream);
+}
+
 }  // namespace
 
-cudaError_t launch_march(const MarchArgs &a, int n_views, bool half_texels, cudaStream_t stream) {
+cudaError_t launch_march(const MarchArgs &a, int n_views, bool half_texels, bool wide_index, cudaStream_t stream) {
     const bool strict = (a.flags & PYVR_FLAG_STRICT) != 0;
-    if (strict) return half_texels ? launch_one<true, true>(a, n_views, stream) : launch_one<true, false>(a, n_views, stream);
-    return half_texels ? launch_one<false, true>(a, n_views, stream) : launch_one<false, false>(a, n_views, stream);
+    if (strict) return half_texels ? launch_idx<true, true>(a, n_views, wide_index, stream)
+                                   : launch_idx<true, false>(a, n_views, wide_index, stream);
+    return half_texels ? launch_idx<false, true>(a, n_views, wide_index, stream)
+                       : launch_idx<false, false>(a, n_views, wide_index, stream);
 }
 
 }  // namespace pyvr

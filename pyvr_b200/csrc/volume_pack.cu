@@ -2,7 +2,7 @@
 //
 //  * pack_texels: fuses the reference's two textures (R32F scalar, RGB32F normal;
 //    pyvr/moderngl_renderer/manager.py:95-101,123-129) into one interleaved texel {s,nx,ny,nz}
-//    (binary32 or binary16) stored in the separable (linear or 8^3-brick) layout of VolumeDesc.
+//    (binary32 or binary16) stored in the line/slot layout of VolumeDesc (common.cuh).
 //    A Volume without normals is packed with normal = (s, 0, 0): that is what the shader samples when
 //    `normal_volume` is left on texture unit 0 (renderer.py:143-146).
 //  * cell_minmax / cell_classify: the macrocell grid for exact empty-space skipping.  A cell is
@@ -12,12 +12,8 @@
 namespace pyvr {
 namespace {
 
-__device__ __forceinline__ long long axis_offset(const AxisMap &m, int i) {
-    return (long long)(i >> m.shift) * m.outer + (long long)(i & m.mask) * m.inner;
-}
-
 // One thread per source voxel, z (memory-fastest in the source) across threadIdx.x: reads are
-// coalesced; writes are coalesced within a brick row (8 texels = 128 B for f32x4) or fully (linear).
+// coalesced; writes fill whole 128-byte lines (a z-run of SLOTS texels, permuted by the slot swizzle).
 template <bool HALF>
 __global__ void __launch_bounds__(256)
 pack_texels_kernel(const float *__restrict__ scalar, const float *__restrict__ normals, VolumeDesc v) {
@@ -35,7 +31,7 @@ pack_texels_kernel(const float *__restrict__ scalar, const float *__restrict__ n
         } else {
             a = s; b = 0.0f; c = 0.0f;
         }
-        const long long at = axis_offset(v.map[0], ix) + axis_offset(v.map[1], iy) + axis_offset(v.map[2], iz);
+        const long long at = texel_index(v, ix, iy, iz);
         if constexpr (HALF) {
             __half2 lo = __floats2half2_rn(s, a), hi = __floats2half2_rn(b, c);
             uint2 raw;
@@ -72,8 +68,7 @@ cell_minmax_kernel(VolumeDesc v, float2 *__restrict__ out) {
         float lo = INFINITY, hi = -INFINITY;
         for (int t = lane; t < wx * wy * wz; t += 32) {
             const int dz = t % wz, dy = (t / wz) % wy, dx = t / (wz * wy);
-            const long long at = axis_offset(v.map[0], x0 + dx) + axis_offset(v.map[1], y0 + dy) +
-                                 axis_offset(v.map[2], z0 + dz);
+            const long long at = texel_index(v, x0 + dx, y0 + dy, z0 + dz);
             const float s = load_scalar<HALF>(v.texels, at);
             // NaN voxels: keep the cell active by poisoning the range
             if (s != s) { lo = -INFINITY; hi = INFINITY; }

@@ -159,7 +159,7 @@ def test_non_cubic_volume():
     want, _, counters = oracle.render(vol, *args)
     got, stats = _render_gpu(vol, *args, strict=True)
     assert image_metrics(got, want)["max_abs"] <= 1 and abs(stats["samples"] - counters["samples"]) <= 16
-    for layout in ("linear", "brick"):
+    for layout in ("linear", "brick", "linear_swz", "brick_swz"):
         os.environ["PYVR_CUDA_LAYOUT"] = layout
         try:
             got, _ = _render_gpu(vol, *args)
@@ -179,12 +179,35 @@ def test_lut_sizes(size):
     assert_parity(got, want)
 
 
-def test_half_texels_within_tolerance(c1):
+@pytest.mark.parametrize("layout", ["linear", "brick", "linear_swz", "brick_swz"])
+def test_half_texels_within_tolerance(c1, layout):
     vol, light, lut = c1
     cam, cfg = Camera.isometric_view(distance=3.0), RenderConfig.balanced()
     want, _, _ = oracle.render(vol, cam, light, cfg, lut, 512, 512)
-    got, _ = _render_gpu(vol, cam, light, cfg, lut, 512, 512, texel_format="f16")
+    os.environ["PYVR_CUDA_LAYOUT"] = layout
+    try:
+        got, _ = _render_gpu(vol, cam, light, cfg, lut, 512, 512, texel_format="f16")
+    finally:
+        del os.environ["PYVR_CUDA_LAYOUT"]
     assert_parity(got, want)
+
+
+@pytest.mark.parametrize("layout", ["linear", "brick", "linear_swz", "brick_swz"])
+def test_layouts_are_bit_identical(c1, layout):
+    """The texel layout only moves bytes around: every layout must give the same float image."""
+    vol, light, lut = c1
+    out = {}
+    for name in ("linear", layout):
+        os.environ["PYVR_CUDA_LAYOUT"] = name
+        try:
+            with VolumeRenderer(200, 120, config=RenderConfig.balanced(), light=light) as r:
+                r.load_volume(vol)
+                r.set_camera(turntable_camera(123))
+                r.set_lut(lut)
+                out[name] = r.render_accum()
+        finally:
+            del os.environ["PYVR_CUDA_LAYOUT"]
+    assert np.array_equal(out["linear"].view(np.uint32), out[layout].view(np.uint32))
 
 
 def test_render_without_volume_or_camera_returns_cleared_frame():
