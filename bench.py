@@ -53,7 +53,7 @@ def parse_args():
     ap.add_argument("--views-per-step", type=int, default=12)
     ap.add_argument("--texels", default="f32", choices=["f32", "f16"])
     ap.add_argument("--no-ess", action="store_true", help="disable empty-space skipping")
-    ap.add_argument("--layout", default=None, choices=["linear", "brick", "linear_swz", "brick_swz"])
+    ap.add_argument("--layout", default=None, choices=["linear", "swizzle"])
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     return ap.parse_args()

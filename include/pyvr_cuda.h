@@ -144,8 +144,8 @@ int pyvr_cuda_compute_normals(int device, const float *in, float *out, int n0, i
                               int buffers_are_device, float *kernel_ms);
 
 /* --- misc ------------------------------------------------------------------------------------------ */
-/* Tuning knobs (no reference counterpart).  "layout": 0 = linear texel array, 1 = 8^3 bricks (default);
- * must be set before pyvr_cuda_upload_volume. */
+/* Tuning knobs (no reference counterpart).  "swizzle": 1 (default) = L1 bank swizzle of the packed texel
+ * layout, 0 = plain rows (for A/B profiling); must be set before pyvr_cuda_upload_volume. */
 int pyvr_cuda_set_option(pyvr_ctx *ctx, const char *key, int value);
 /* Page-locked host memory for frame read-back at full PCIe rate (cudaMallocHost / cudaFreeHost). */
 int pyvr_cuda_host_alloc(size_t bytes, void **out);

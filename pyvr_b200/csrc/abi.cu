@@ -63,9 +63,10 @@ struct pyvr_ctx {
     bool have_volume = false;
     VolumeDesc vol{};
     float2 *cell_minmax = nullptr;
-    uint8_t *cell_active = nullptr;
+    uint8_t *cell_dist = nullptr, *cell_scratch = nullptr;   // distance map + ping-pong buffer
+    int *active_box = nullptr;     // 6 ints, see VolumeDesc
     size_t n_cells = 0;
-    int layout = 2;  // bit 0: 8x8 bricks of lines (else plain rows); bit 1: slot swizzle
+    bool swizzle = true;  // L1 bank swizzle of the texel layout (common.cuh); off only for A/B profiling
 
     // transfer function
     float4 *lut = nullptr;
@@ -164,45 +165,34 @@ void fill_volume_desc(pyvr_ctx *c, int shape0, int shape1, int shape2, const flo
         v.voff[a] = (float)(-(double)bmin[a] * (double)v.n[a] / ext - 0.5);
         v.ncell[a] = (v.n[a] + 7) / 8;
     }
-    // lines of SLOTS consecutive-z texels; see common.cuh
+    // lines of SLOTS consecutive-z texels with an optional slot rotation; see common.cuh
     v.slot_shift = c->half_texels ? 4 : 3;
-    const long long nzl = (v.n[2] + (1 << v.slot_shift) - 1) >> v.slot_shift;   // lines per z-row
-    if (c->layout & 1) {      // 8x8 bricks of lines
-        const long long nby = v.ncell[1];
-        v.map[0] = {3, 7, nby * nzl * 64, 8};
-        v.map[1] = {3, 7, nzl * 64, 1};
-        v.map[2] = {v.slot_shift, 0, 64, 0};
-    } else {                  // plain rows
-        v.map[0] = {31, 0x7fffffff, 0, (long long)v.n[1] * nzl};
-        v.map[1] = {31, 0x7fffffff, 0, nzl};
-        v.map[2] = {v.slot_shift, 0, 1, 0};
-    }
-    const bool swizzle = (c->layout & 2) != 0;
-    v.swz[0] = swizzle ? 1 : 0;
-    v.swz[1] = swizzle ? 3 : 0;
+    v.row_lines = (v.n[2] + (1 << v.slot_shift) - 1) >> v.slot_shift;
+    v.swz_x = c->swizzle ? 1 : 0;
+    v.swz_y = c->swizzle ? 3 : 0;
 }
 
 size_t texel_count(const pyvr_ctx *c) {
     const VolumeDesc &v = c->vol;
-    const size_t slots = (size_t)1 << v.slot_shift;
-    const size_t nzl = ((size_t)v.n[2] + slots - 1) >> v.slot_shift;
-    if (c->layout & 1) return (size_t)v.ncell[0] * v.ncell[1] * 64 * nzl * slots;
-    return (size_t)v.n[0] * v.n[1] * nzl * slots;
+    return ((size_t)v.n[0] * v.n[1] * v.row_lines) << v.slot_shift;
 }
 
 int classify_cells(pyvr_ctx *c) {
     if (!c->have_volume || c->lut_size <= 0) return PYVR_OK;
-    CU(launch_cell_classify(c->cell_minmax, c->n_cells, c->lut, c->lut_size, c->cell_active, c->stream));
+    CU(launch_cell_classify(c->cell_minmax, c->vol, c->lut, c->lut_size, c->cell_dist, c->cell_scratch, c->active_box, c->stream));
     return PYVR_OK;
 }
 
 void free_volume(pyvr_ctx *c) {
     cudaFree(c->texels); c->texels = nullptr;
     cudaFree(c->cell_minmax); c->cell_minmax = nullptr;
-    cudaFree(c->cell_active); c->cell_active = nullptr;
+    cudaFree(c->cell_dist); c->cell_dist = nullptr;
+    cudaFree(c->cell_scratch); c->cell_scratch = nullptr;
+    cudaFree(c->active_box); c->active_box = nullptr;
     c->have_volume = false;
     c->vol.texels = nullptr;
-    c->vol.cell_active = nullptr;
+    c->vol.cell_dist = nullptr;
+    c->vol.active_box = nullptr;
 }
 
 int ensure_views(pyvr_ctx *c, int n) {
@@ -311,12 +301,7 @@ int pyvr_cuda_create(int device, int width, int height, pyvr_ctx **out_ctx) {
     c->width = width;
     c->height = height;
     const char *layout = getenv("PYVR_CUDA_LAYOUT");
-    if (layout) {
-        if (strcmp(layout, "linear") == 0) c->layout = 0;
-        else if (strcmp(layout, "brick") == 0) c->layout = 1;
-        else if (strcmp(layout, "linear_swz") == 0) c->layout = 2;
-        else if (strcmp(layout, "brick_swz") == 0) c->layout = 3;
-    }
+    if (layout) c->swizzle = strcmp(layout, "linear") != 0;   // "linear" = no swizzle, anything else = default
     // defaults of the reference renderer: balanced preset, Light.default(), bounds +-0.5
     c->params.step_size = 0.01f; c->params.max_steps = 500; c->params.reference_step_size = 0.01f;
     c->params.ambient = 0.2f; c->params.diffuse = 0.8f;
@@ -373,11 +358,10 @@ int pyvr_cuda_set_stream(pyvr_ctx *c, void *cuda_stream) {
 
 int pyvr_cuda_set_option(pyvr_ctx *c, const char *key, int value) {
     if (!c || !key) return fail(PYVR_ERR_INVALID, "ctx or key is NULL");
-    if (strcmp(key, "layout") == 0) {
-        if (value < 0 || value > 3) return fail(PYVR_ERR_INVALID, "layout must be 0..3 (bit 0 bricks, bit 1 swizzle)");
-        if (c->have_volume && value != c->layout)
-            return fail(PYVR_ERR_STATE, "layout must be chosen before the volume is uploaded");
-        c->layout = value;
+    if (strcmp(key, "swizzle") == 0) {
+        if (c->have_volume && (value != 0) != c->swizzle)
+            return fail(PYVR_ERR_STATE, "swizzle must be chosen before the volume is uploaded");
+        c->swizzle = value != 0;
         return PYVR_OK;
     }
     return fail(PYVR_ERR_INVALID, "unknown option '%s'", key);
@@ -405,10 +389,13 @@ int pyvr_cuda_upload_volume(pyvr_ctx *c, const float *scalar, const float *norma
     c->n_cells = (size_t)c->vol.ncell[0] * c->vol.ncell[1] * c->vol.ncell[2];
     CU(cudaMalloc(&c->texels, c->texel_bytes));
     CU(cudaMalloc(&c->cell_minmax, c->n_cells * sizeof(float2)));
-    CU(cudaMalloc(&c->cell_active, c->n_cells));
+    CU(cudaMalloc(&c->cell_dist, c->n_cells));
+    CU(cudaMalloc(&c->cell_scratch, c->n_cells));
+    CU(cudaMalloc(&c->active_box, 6 * sizeof(int)));
     if (n_tex != voxels) CU(cudaMemsetAsync(c->texels, 0, c->texel_bytes, c->stream));
     c->vol.texels = c->texels;
-    c->vol.cell_active = c->cell_active;
+    c->vol.cell_dist = c->cell_dist;
+    c->vol.active_box = c->active_box;
 
     const float *d_scalar = scalar, *d_normals = normals;
     float *stage_s = nullptr, *stage_n = nullptr;

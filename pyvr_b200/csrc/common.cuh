@@ -1,9 +1,8 @@
-// common.cuh -- shared declarations of the sm_100a backend (device-side structs, error plumbing).
+// common.cuh -- shared declarations of the sm_100a backend (device-side structs, launch prototypes).
 //
 // Built with -fmad=false: the compiler never contracts a*b+c on its own, so the only fused
-// operations are the explicit fmaf()/__fmaf_rn() calls in the kernels.  That makes the arithmetic
-// of the STRICT path a statement-by-statement twin of oracle/pyvr_oracle.c (DESIGN.md,
-// "Arithmetic contract").
+// operations are the explicit fmaf() calls in the kernels.  That makes the arithmetic of the STRICT
+// path a statement-by-statement twin of oracle/pyvr_oracle.c ("Arithmetic contract").
 #pragma once
 
 #include <cuda_fp16.h>
@@ -14,44 +13,38 @@
 
 namespace pyvr {
 
-// Address map of the packed texel array.  Texels live in 128-byte lines of SLOTS = 128/texel_bytes
-// consecutive-z texels (8 for f32x4, 16 for f16x4):
-//   line(ix,iy,iz)  = off_x(ix) + off_y(iy) + off_z(iz),   off_a(i) = (i >> shift)*outer + (i & mask)*inner
-//   slot(ix,iy,iz)  = (iz + swz[0]*ix + swz[1]*iy) & (SLOTS-1)
-//   texel index     = line * SLOTS + slot
-// The separable line map covers plain rows (x,y linear) and 8x8 bricks of lines.  The slot rotation
-// ("swizzle") permutes texels inside their line so that the texels one warp-wide load touches -- a
-// small planar patch, typically many (x,y) rows at the same z -- spread over the L1 data banks
-// instead of all landing on the banks of one slot ("L1 bank swizzle").
-struct AxisMap {
-    int shift;
-    int mask;
-    long long outer;
-    long long inner;
-};
-
+// Packed texel array.  Texels {s,nx,ny,nz} live in 128-byte lines of SLOTS = 128/texel_bytes
+// consecutive-z texels (8 for f32x4, 16 for f16x4); lines are ordered x-major, then y, then z:
+//   line(ix,iy,iz) = (ix*n[1] + iy) * row_lines + (iz >> slot_shift)
+//   slot(ix,iy,iz) = (iz + swz_x*ix + swz_y*iy) & (SLOTS-1)
+//   texel index    = line * SLOTS + slot
+// The slot rotation ("swizzle") permutes texels inside their line.  One warp-wide corner load touches
+// a small planar patch of texels, typically many (x,y) rows at the same z; without the rotation they
+// all sit in the same slot of different lines, i.e. on the same L1 data banks, and the load
+// serialises into one data-stage wavefront per texel (measured: 18.6 wavefronts per LDG.128,
+// l1tex data pipe at 99 %).  With it they spread over the banks ("L1 bank swizzle").
 struct VolumeDesc {
     const void *texels;   // float4 {s,nx,ny,nz} or 4 x half
     int n[3];             // texel counts along world x, y, z.  NB world z is the memory-fastest axis
                           // of the array the reference uploads: (nz, ny, nx) = numpy shape (0, 1, 2).
-    AxisMap map[3];       // line offsets (see above)
     int slot_shift;       // log2(SLOTS): 3 for f32x4, 4 for f16x4
-    int swz[2];           // slot rotation multipliers for ix, iy (0, 0 = no swizzle)
+    int row_lines;        // lines per z-row = ceil(n[2] / SLOTS)
+    int swz_x, swz_y;     // slot rotation multipliers (0, 0 = no swizzle)
     float bmin[3], bmax[3];
     // fast path: voxel coordinate = world * vscale + voff  (= tc * n - 0.5)
     float vscale[3], voff[3];
-    // empty-space skipping: one byte per 8^3 macrocell, 1 = some sample in it may have alpha != 0
-    const uint8_t *cell_active;
+    // empty-space skipping: one byte per 8^3 macrocell = chessboard distance (in cells, capped) to the
+    // nearest cell in which some sample may have alpha != 0 (0 = this cell is active), and the bounding
+    // box of the active cells {lo_x, lo_y, lo_z, hi_x, hi_y, hi_z} in cell units (hi inclusive; lo > hi
+    // when no cell is active).  Both are written by launch_cell_classify.
+    const uint8_t *cell_dist;
+    const int *active_box;
     int ncell[3];
 };
 
-__host__ __device__ __forceinline__ long long axis_offset(const AxisMap &m, int i) {
-    return (long long)(i >> m.shift) * m.outer + (long long)(i & m.mask) * m.inner;
-}
-
 __host__ __device__ __forceinline__ long long texel_index(const VolumeDesc &v, int ix, int iy, int iz) {
-    const long long line = axis_offset(v.map[0], ix) + axis_offset(v.map[1], iy) + axis_offset(v.map[2], iz);
-    const int slot = (iz + v.swz[0] * ix + v.swz[1] * iy) & ((1 << v.slot_shift) - 1);
+    const long long line = ((long long)ix * v.n[1] + iy) * v.row_lines + (iz >> v.slot_shift);
+    const int slot = (iz + v.swz_x * ix + v.swz_y * iy) & ((1 << v.slot_shift) - 1);
     return (line << v.slot_shift) + slot;
 }
 
@@ -82,8 +75,10 @@ cudaError_t launch_pack_texels(const float *scalar, const float *normals, const 
                                bool half_texels, cudaStream_t stream);
 cudaError_t launch_cell_minmax(const VolumeDesc &vol, bool half_texels, float2 *cell_minmax,
                                cudaStream_t stream);
-cudaError_t launch_cell_classify(const float2 *cell_minmax, size_t n_cells, const float4 *lut,
-                                 int lut_size, uint8_t *cell_active, cudaStream_t stream);
+constexpr int kCellDistSweeps = 16;   // distance values above this are only lower bounds (still safe)
+cudaError_t launch_cell_classify(const float2 *cell_minmax, const VolumeDesc &vol, const float4 *lut,
+                                 int lut_size, uint8_t *cell_dist, uint8_t *cell_scratch, int *active_box,
+                                 cudaStream_t stream);
 cudaError_t launch_normals(const float *in, float *out, int n0, int n1, int n2, cudaStream_t stream);
 
 }  // namespace pyvr

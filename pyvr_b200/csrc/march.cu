@@ -10,12 +10,15 @@
 // texel array (L1 does the gather amplification, L2/HBM stream each touched line once).  The RGBA
 // transfer-function LUT is staged in shared memory once per CTA.
 //
-// Two arithmetic modes (MarchArgs.flags):
+// Ray set-up (direction, slab test, entry point, validity of the entry sample) uses the oracle's
+// arithmetic in both modes.  After that there are two arithmetic modes (MarchArgs.flags):
 //   STRICT  statement-by-statement twin of the oracle: incremental position p += dir*step, IEEE
 //           divide / sqrt / expf, no skipping.  Used to pin the kernel against oracle/pyvr_oracle.c.
-//   fast    (default) the same sample lattice evaluated directly in voxel space
-//           x(i) = X0 + i*DX (one FMA per axis), ex2.approx / rsqrt.approx, optional exact
-//           empty-space skipping over 8^3 macrocells.  Differences to STRICT are ~1e-6 relative.
+//   fast    (default) the same sample lattice evaluated directly in voxel space,
+//           x(i) = X0 + i*DX (one FMA per axis): the in-volume index range [i_lo, i_hi] is found once
+//           per ray, clipped to the bounding box of the active macrocells, and marched with exact
+//           empty-space skipping over 8^3 macrocells; ex2.approx / rsqrt.approx.  Differences to
+//           STRICT are ~1e-6 relative.
 #include "common.cuh"
 
 namespace pyvr {
@@ -69,26 +72,27 @@ struct Corner8 {
     float4 c[8];  // index = (x_tap << 2) | (y_tap << 1) | z_tap
 };
 
-// Eight corner fetches.  IDX is int (packed array < 2^31 texels) or long long.
+// Eight corner fetches from the line/slot layout of common.cuh.  IDX is int (packed array < 2^31
+// texels) or long long.
 template <bool HALF, typename IDX>
 __device__ __forceinline__ Corner8 gather(const VolumeDesc &v, const Taps &tx, const Taps &ty, const Taps &tz) {
     constexpr int LS = HALF ? 4 : 3, SLOT_MASK = (1 << LS) - 1;
-    const IDX ox0 = (IDX)axis_offset(v.map[0], tx.i0), ox1 = (IDX)axis_offset(v.map[0], tx.i1);
-    const IDX oy0 = (IDX)axis_offset(v.map[1], ty.i0), oy1 = (IDX)axis_offset(v.map[1], ty.i1);
-    const IDX oz0 = (IDX)axis_offset(v.map[2], tz.i0), oz1 = (IDX)axis_offset(v.map[2], tz.i1);
-    const int sx0 = v.swz[0] * tx.i0, sx1 = v.swz[0] * tx.i1, sy0 = v.swz[1] * ty.i0, sy1 = v.swz[1] * ty.i1;
-    const IDX l00 = ox0 + oy0, l01 = ox0 + oy1, l10 = ox1 + oy0, l11 = ox1 + oy1;
+    const IDX rx0 = (IDX)tx.i0 * v.n[1], rx1 = (IDX)tx.i1 * v.n[1];
+    const IDX l00 = (rx0 + ty.i0) * v.row_lines, l01 = (rx0 + ty.i1) * v.row_lines;
+    const IDX l10 = (rx1 + ty.i0) * v.row_lines, l11 = (rx1 + ty.i1) * v.row_lines;
+    const int lz0 = tz.i0 >> LS, lz1 = tz.i1 >> LS;
+    const int sx0 = v.swz_x * tx.i0, sx1 = v.swz_x * tx.i1, sy0 = v.swz_y * ty.i0, sy1 = v.swz_y * ty.i1;
     const int s00 = sx0 + sy0, s01 = sx0 + sy1, s10 = sx1 + sy0, s11 = sx1 + sy1;
-#define PYVR_AT(l, s, oz, iz) ((((l) + (oz)) << LS) + (IDX)(((s) + (iz)) & SLOT_MASK))
+#define PYVR_AT(l, s, lz, iz) ((((l) + (lz)) << LS) + (IDX)(((s) + (iz)) & SLOT_MASK))
     Corner8 r;
-    r.c[0] = load_texel<HALF, IDX>(v.texels, PYVR_AT(l00, s00, oz0, tz.i0));
-    r.c[1] = load_texel<HALF, IDX>(v.texels, PYVR_AT(l00, s00, oz1, tz.i1));
-    r.c[2] = load_texel<HALF, IDX>(v.texels, PYVR_AT(l01, s01, oz0, tz.i0));
-    r.c[3] = load_texel<HALF, IDX>(v.texels, PYVR_AT(l01, s01, oz1, tz.i1));
-    r.c[4] = load_texel<HALF, IDX>(v.texels, PYVR_AT(l10, s10, oz0, tz.i0));
-    r.c[5] = load_texel<HALF, IDX>(v.texels, PYVR_AT(l10, s10, oz1, tz.i1));
-    r.c[6] = load_texel<HALF, IDX>(v.texels, PYVR_AT(l11, s11, oz0, tz.i0));
-    r.c[7] = load_texel<HALF, IDX>(v.texels, PYVR_AT(l11, s11, oz1, tz.i1));
+    r.c[0] = load_texel<HALF, IDX>(v.texels, PYVR_AT(l00, s00, lz0, tz.i0));
+    r.c[1] = load_texel<HALF, IDX>(v.texels, PYVR_AT(l00, s00, lz1, tz.i1));
+    r.c[2] = load_texel<HALF, IDX>(v.texels, PYVR_AT(l01, s01, lz0, tz.i0));
+    r.c[3] = load_texel<HALF, IDX>(v.texels, PYVR_AT(l01, s01, lz1, tz.i1));
+    r.c[4] = load_texel<HALF, IDX>(v.texels, PYVR_AT(l10, s10, lz0, tz.i0));
+    r.c[5] = load_texel<HALF, IDX>(v.texels, PYVR_AT(l10, s10, lz1, tz.i1));
+    r.c[6] = load_texel<HALF, IDX>(v.texels, PYVR_AT(l11, s11, lz0, tz.i0));
+    r.c[7] = load_texel<HALF, IDX>(v.texels, PYVR_AT(l11, s11, lz1, tz.i1));
 #undef PYVR_AT
     return r;
 }
@@ -140,6 +144,18 @@ __device__ __forceinline__ void shade(const MarchArgs &a, const float4 *s_lut, c
     acc.g = fmaf(t, cg * light * alpha, acc.g);
     acc.b = fmaf(t, cb * light * alpha, acc.b);
     acc.a = fmaf(t, alpha, acc.a);
+}
+
+// Index interval on which lo <= X0 + i*D <= hi, intersected into [enter, exit].
+__device__ __forceinline__ void index_slab(float X0, float D, float lo, float hi, float &enter, float &exit) {
+    if (D != 0.0f) {
+        const float r = 1.0f / D, a = (lo - X0) * r, b = (hi - X0) * r;
+        enter = fmaxf(enter, fminf(a, b));
+        exit = fminf(exit, fmaxf(a, b));
+    } else if (X0 < lo || X0 > hi) {
+        enter = 3.0e38f;
+        exit = -3.0e38f;
+    }
 }
 
 template <bool STRICT, bool HALF, typename IDX>
@@ -221,8 +237,8 @@ march_kernel(const __grid_constant__ MarchArgs a) {
                 }
                 terminated = (i < n_steps) || (n_steps < a.max_steps && acc.a >= a.term_alpha);
             } else {
-                // voxel-space lattice: x(i) = X0 + i*DX, valid iff -0.5 <= x <= n-0.5 on every axis;
-                // sample 0 (on the box surface) takes the reference's own validity test instead.
+                // ---- voxel-space lattice x(i) = X0 + i*DX; sample i is valid iff -0.5 <= x <= n-0.5 on
+                // every axis, except sample 0 (on the box surface), which takes the reference's own test.
                 const float t0x = (p0x - vol.bmin[0]) / (vol.bmax[0] - vol.bmin[0]);
                 const float t0y = (p0y - vol.bmin[1]) / (vol.bmax[1] - vol.bmin[1]);
                 const float t0z = (p0z - vol.bmin[2]) / (vol.bmax[2] - vol.bmin[2]);
@@ -231,47 +247,87 @@ march_kernel(const __grid_constant__ MarchArgs a) {
                 const float Y0 = fmaf(p0y, vol.vscale[1], vol.voff[1]), DY = sy * vol.vscale[1];
                 const float Z0 = fmaf(p0z, vol.vscale[2], vol.voff[2]), DZ = sz * vol.vscale[2];
                 const float hx = (float)vol.n[0] - 0.5f, hy = (float)vol.n[1] - 0.5f, hz = (float)vol.n[2] - 0.5f;
-                const bool ess = (a.flags & PYVR_FLAG_ESS) && vol.cell_active != nullptr;
-                const float rDX = 1.0f / DX, rDY = 1.0f / DY, rDZ = 1.0f / DZ;
-                int i = 0;
-                while (i < n_steps) {
+                auto valid = [&](int i) -> bool {
+                    if (i <= 0) return i == 0 && valid0;
+                    if (i >= n_steps) return false;
                     const float fi = (float)i;
-                    float x = fmaf(fi, DX, X0), y = fmaf(fi, DY, Y0), z = fmaf(fi, DZ, Z0);
-                    bool valid = x >= -0.5f && x <= hx && y >= -0.5f && y <= hy && z >= -0.5f && z <= hz;
-                    if (i == 0) {
-                        valid = valid0;
-                        x = fminf(fmaxf(x, -0.5f), hx); y = fminf(fmaxf(y, -0.5f), hy); z = fminf(fmaxf(z, -0.5f), hz);
+                    const float x = fmaf(fi, DX, X0), y = fmaf(fi, DY, Y0), z = fmaf(fi, DZ, Z0);
+                    return x >= -0.5f && x <= hx && y >= -0.5f && y <= hy && z >= -0.5f && z <= hz;
+                };
+
+                // in-volume index range [i_lo, i_hi]: slab estimate, then the predicate is the arbiter
+                float enter = -3.0e38f, exit = 3.0e38f;
+                index_slab(X0, DX, -0.5f, hx, enter, exit);
+                index_slab(Y0, DY, -0.5f, hy, enter, exit);
+                index_slab(Z0, DZ, -0.5f, hz, enter, exit);
+                int i_lo = (int)fminf(fmaxf(ceilf(enter), 0.0f), (float)n_steps);
+                int i_hi = (int)fminf(fmaxf(floorf(exit), -1.0f), (float)(n_steps - 1));
+                if (valid(i_lo - 1)) --i_lo; else if (!valid(i_lo)) ++i_lo;
+                if (valid(i_hi + 1)) ++i_hi; else if (!valid(i_hi)) --i_hi;
+                if (valid0) i_lo = 0;
+                else if (i_lo == 0) i_lo = 1;
+
+                // clip to the bounding box of the active macrocells (samples outside add exactly zero)
+                const bool ess = (a.flags & PYVR_FLAG_ESS) && vol.cell_dist != nullptr;
+                int j_lo = i_lo, j_hi = i_hi;
+                if (ess) {
+                    const int *ab = vol.active_box;
+                    const int cx0 = __ldg(ab + 0), cy0 = __ldg(ab + 1), cz0 = __ldg(ab + 2);
+                    const int cx1 = __ldg(ab + 3), cy1 = __ldg(ab + 4), cz1 = __ldg(ab + 5);
+                    if (cx0 > cx1) {
+                        j_hi = j_lo - 1;
+                    } else {
+                        float en = -3.0e38f, exi = 3.0e38f;
+                        index_slab(X0, DX, cx0 == 0 ? -0.5f : (float)(8 * cx0), fminf((float)(8 * cx1 + 8), hx), en, exi);
+                        index_slab(Y0, DY, cy0 == 0 ? -0.5f : (float)(8 * cy0), fminf((float)(8 * cy1 + 8), hy), en, exi);
+                        index_slab(Z0, DZ, cz0 == 0 ? -0.5f : (float)(8 * cz0), fminf((float)(8 * cz1 + 8), hz), en, exi);
+                        j_lo = max(j_lo, (int)fminf(fmaxf(floorf(en) - 1.0f, 0.0f), (float)n_steps));
+                        j_hi = min(j_hi, (int)fminf(fmaxf(ceilf(exi) + 1.0f, -1.0f), (float)n_steps));
                     }
-                    if (valid) {
-                        const Taps tx = voxel_taps(x, vol.n[0]), ty = voxel_taps(y, vol.n[1]),
-                                   tz = voxel_taps(z, vol.n[2]);
-                        if (ess) {
-                            const int cx = tx.i0 >> 3, cy = ty.i0 >> 3, cz = tz.i0 >> 3;
-                            const uint8_t active =
-                                __ldg(vol.cell_active + ((size_t)cx * vol.ncell[1] + cy) * vol.ncell[2] + cz);
-                            if (!active) {
-                                // Whole steps that stay inside this cell (and inside the volume) on every
-                                // axis, conservative by 0.01 step.  A zero direction component never exits.
-                                const float ex = ((DX > 0.0f ? fminf((float)(8 * cx + 8), hx) : fmaxf((float)(8 * cx), -0.5f)) - x) * rDX;
-                                const float ey = ((DY > 0.0f ? fminf((float)(8 * cy + 8), hy) : fmaxf((float)(8 * cy), -0.5f)) - y) * rDY;
-                                const float ez = ((DZ > 0.0f ? fminf((float)(8 * cz + 8), hz) : fmaxf((float)(8 * cz), -0.5f)) - z) * rDZ;
-                                const float tmin = fminf(fminf(DX != 0.0f ? ex : 3.0e38f, DY != 0.0f ? ey : 3.0e38f),
-                                                         DZ != 0.0f ? ez : 3.0e38f);
-                                int skip = (int)fminf(floorf(tmin - 0.01f), (float)(n_steps - i));
-                                skip = max(skip, 1);
-                                n_samples += skip;
-                                i += skip;
-                                continue;
-                            }
+                }
+
+                const float rDX = 1.0f / DX, rDY = 1.0f / DY, rDZ = 1.0f / DZ;
+                int i = j_lo, last = i_hi;        // `last` = index of the last sample the reference executes
+                int cell_end = ess ? j_lo : 0x7fffffff;   // first index not known to be in an active cell
+                while (true) {
+                    // phase 1: advance this ray to its next sample in an active cell
+                    Taps tx, ty, tz;
+                    bool have = false;
+                    while (i <= j_hi) {
+                        const float fi = (float)i;
+                        float x = fmaf(fi, DX, X0), y = fmaf(fi, DY, Y0), z = fmaf(fi, DZ, Z0);
+                        if (i == 0) {   // valid by the reference's test; keep the taps inside the array
+                            x = fminf(fmaxf(x, -0.5f), hx); y = fminf(fmaxf(y, -0.5f), hy); z = fminf(fmaxf(z, -0.5f), hz);
                         }
-                        ++n_samples; ++n_fetched;
-                        const Corner8 k = gather<HALF, IDX>(vol, tx, ty, tz);
-                        shade<false>(a, s_lut, k, tx.f, ty.f, tz.f, acc);
-                        if (acc.a >= a.term_alpha) { terminated = true; break; }
+                        tx = voxel_taps(x, vol.n[0]); ty = voxel_taps(y, vol.n[1]); tz = voxel_taps(z, vol.n[2]);
+                        if (i < cell_end) { have = true; break; }
+                        const int cx = tx.i0 >> 3, cy = ty.i0 >> 3, cz = tz.i0 >> 3;
+                        // d = 0: active cell.  d > 0: every cell within chessboard radius d-1 is inactive, so
+                        // the ray may run to the faces of that cube of cells.  Either way: whole steps that
+                        // stay inside (and inside the volume) on every axis, conservative by 0.01 step; a
+                        // zero direction component never exits.
+                        const int d = __ldg(vol.cell_dist + ((size_t)cx * vol.ncell[1] + cy) * vol.ncell[2] + cz);
+                        const int r = max(d - 1, 0);
+                        const float ex = ((DX > 0.0f ? fminf((float)(8 * (cx + r) + 8), hx) : fmaxf((float)(8 * (cx - r)), -0.5f)) - x) * rDX;
+                        const float ey = ((DY > 0.0f ? fminf((float)(8 * (cy + r) + 8), hy) : fmaxf((float)(8 * (cy - r)), -0.5f)) - y) * rDY;
+                        const float ez = ((DZ > 0.0f ? fminf((float)(8 * (cz + r) + 8), hz) : fmaxf((float)(8 * (cz - r)), -0.5f)) - z) * rDZ;
+                        const float tmin = fminf(fminf(DX != 0.0f ? ex : 3.0e38f, DY != 0.0f ? ey : 3.0e38f),
+                                                 DZ != 0.0f ? ez : 3.0e38f);
+                        const int stay = max((int)fminf(floorf(tmin - 0.01f), 1.0e6f), 1);
+                        const bool active = d == 0;
+                        if (active) { cell_end = i + stay; have = true; break; }
+                        i += stay;
                     }
+                    if (!have) break;
+                    // phase 2: every lane still here has a sample to fetch
+                    ++n_fetched;
+                    const Corner8 k = gather<HALF, IDX>(vol, tx, ty, tz);
+                    shade<false>(a, s_lut, k, tx.f, ty.f, tz.f, acc);
+                    if (acc.a >= a.term_alpha) { terminated = true; last = i; break; }
                     ++i;
                 }
-                if (terminated && i + 1 >= a.max_steps) terminated = false;
+                n_samples = (unsigned)max(last - i_lo + 1, 0);
+                if (terminated && last + 1 >= a.max_steps) terminated = false;
             }
         }
     }

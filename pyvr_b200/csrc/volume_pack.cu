@@ -5,8 +5,9 @@
 //    (binary32 or binary16) stored in the line/slot layout of VolumeDesc (common.cuh).
 //    A Volume without normals is packed with normal = (s, 0, 0): that is what the shader samples when
 //    `normal_volume` is left on texture unit 0 (renderer.py:143-146).
-//  * cell_minmax / cell_classify: the macrocell grid for exact empty-space skipping.  A cell is
-//    inactive only if every sample whose lower taps fall in it provably has alpha_tf == 0.
+//  * cell_minmax / cell_classify / cell_dist_relax: the macrocell grid for exact empty-space skipping.
+//    A cell is inactive only if every sample whose lower taps fall in it provably has alpha_tf == 0;
+//    inactive cells then get their chessboard distance to the nearest active cell.
 #include "common.cuh"
 
 namespace pyvr {
@@ -88,9 +89,10 @@ cell_minmax_kernel(VolumeDesc v, float2 *__restrict__ out) {
 // march uses: binary32 multiply/subtract are monotonic, hence floor(x(d)) lies between the two ends.
 // The cell is inactive iff every LUT alpha in that tap range is exactly zero.
 __global__ void __launch_bounds__(256)
-cell_classify_kernel(const float2 *__restrict__ mm, size_t n_cells, const float4 *__restrict__ lut,
-                     int lut_size, uint8_t *__restrict__ active) {
+cell_classify_kernel(const float2 *__restrict__ mm, VolumeDesc v, const float4 *__restrict__ lut,
+                     int lut_size, uint8_t *__restrict__ active, int *__restrict__ active_box) {
     extern __shared__ int s_nonzero_before[];  // [j] = number of nonzero alphas in lut[0..j)
+    __shared__ int s_box[6];
     if (threadIdx.x == 0) {
         int run = 0;
         for (int j = 0; j < lut_size; ++j) {
@@ -98,8 +100,11 @@ cell_classify_kernel(const float2 *__restrict__ mm, size_t n_cells, const float4
             run += (lut[j].w != 0.0f) ? 1 : 0;  // NaN != 0 is true: stays active
         }
         s_nonzero_before[lut_size] = run;
+        s_box[0] = s_box[1] = s_box[2] = 0x7fffffff;
+        s_box[3] = s_box[4] = s_box[5] = -1;
     }
     __syncthreads();
+    const size_t n_cells = (size_t)v.ncell[0] * v.ncell[1] * v.ncell[2];
     for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_cells;
          c += (size_t)gridDim.x * blockDim.x) {
         const float2 r = mm[c];
@@ -109,8 +114,58 @@ cell_classify_kernel(const float2 *__restrict__ mm, size_t n_cells, const float4
         const float xl = floorf(lo * size - 0.5f), xh = floorf(hi * size - 0.5f) + 1.0f;
         const int jl = (int)fminf(fmaxf(xl, 0.0f), size - 1.0f);   // NaN/-inf -> 0, +inf -> size-1
         const int jh = (int)fminf(fmaxf(xh, 0.0f), size - 1.0f);
-        active[c] = (s_nonzero_before[jh + 1] - s_nonzero_before[jl]) != 0 ? 1 : 0;
+        const bool on = (s_nonzero_before[jh + 1] - s_nonzero_before[jl]) != 0;
+        active[c] = on ? 0 : 255;   // seed of the distance map: 0 = active, 255 = "far"
+        if (on) {   // bounding box of the active cells, block-local first
+            const int cz = (int)(c % v.ncell[2]);
+            const size_t rest = c / v.ncell[2];
+            const int cy = (int)(rest % v.ncell[1]), cx = (int)(rest / v.ncell[1]);
+            atomicMin(&s_box[0], cx); atomicMin(&s_box[1], cy); atomicMin(&s_box[2], cz);
+            atomicMax(&s_box[3], cx); atomicMax(&s_box[4], cy); atomicMax(&s_box[5], cz);
+        }
     }
+    __syncthreads();
+    if (threadIdx.x < 3) atomicMin(active_box + threadIdx.x, s_box[threadIdx.x]);
+    else if (threadIdx.x < 6) atomicMax(active_box + threadIdx.x, s_box[threadIdx.x]);
+}
+
+// One relaxation sweep of the chessboard (Chebyshev) distance to the nearest active cell, in cells,
+// capped at 255: out = min(in, 1 + min over the 26 neighbours).  After k sweeps every value <= k is
+// final.  A cell with distance d > 0 guarantees that all cells within Chebyshev radius d-1 are inactive,
+// so a ray inside it may jump to the faces of that (2d-1)^3 cube of cells in one step.
+__global__ void __launch_bounds__(256)
+cell_dist_relax_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, int n0, int n1, int n2) {
+    const long long total = (long long)n0 * n1 * n2;
+    for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < total;
+         c += (long long)gridDim.x * blockDim.x) {
+        const int cz = (int)(c % n2);
+        const long long rest = c / n2;
+        const int cy = (int)(rest % n1), cx = (int)(rest / n1);
+        int best = in[c];
+        if (best > 0) {
+            int nb = 255;
+            for (int dx = -1; dx <= 1; ++dx) {
+                const int x = cx + dx;
+                if (x < 0 || x >= n0) continue;
+                for (int dy = -1; dy <= 1; ++dy) {
+                    const int y = cy + dy;
+                    if (y < 0 || y >= n1) continue;
+                    for (int dz = -1; dz <= 1; ++dz) {
+                        const int z = cz + dz;
+                        if (z < 0 || z >= n2) continue;
+                        nb = min(nb, (int)in[((long long)x * n1 + y) * n2 + z]);
+                    }
+                }
+            }
+            best = min(best, nb + 1);
+        }
+        out[c] = (uint8_t)min(best, 255);
+    }
+}
+
+__global__ void reset_active_box_kernel(int *active_box) {
+    if (threadIdx.x < 3) active_box[threadIdx.x] = 0x7fffffff;
+    else if (threadIdx.x < 6) active_box[threadIdx.x] = -1;
 }
 
 inline int grid_for(long long work, int block, int max_blocks = 148 * 16) {
@@ -138,16 +193,25 @@ cudaError_t launch_cell_minmax(const VolumeDesc &vol, bool half_texels, float2 *
     return cudaGetLastError();
 }
 
-cudaError_t launch_cell_classify(const float2 *cell_minmax, size_t n_cells, const float4 *lut,
-                                 int lut_size, uint8_t *cell_active, cudaStream_t stream) {
-    const int grid = grid_for((long long)n_cells, 256, 148 * 4);
+cudaError_t launch_cell_classify(const float2 *cell_minmax, const VolumeDesc &vol, const float4 *lut,
+                                 int lut_size, uint8_t *cell_dist, uint8_t *cell_scratch, int *active_box,
+                                 cudaStream_t stream) {
+    const long long n_cells = (long long)vol.ncell[0] * vol.ncell[1] * vol.ncell[2];
+    const int grid = grid_for(n_cells, 256, 148 * 4);
     const size_t smem = (size_t)(lut_size + 1) * sizeof(int);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(cell_classify_kernel,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    cell_classify_kernel<<<grid, 256, smem, stream>>>(cell_minmax, n_cells, lut, lut_size, cell_active);
+    reset_active_box_kernel<<<1, 32, 0, stream>>>(active_box);
+    cell_classify_kernel<<<grid, 256, smem, stream>>>(cell_minmax, vol, lut, lut_size, cell_dist, active_box);
+    // distance map: kCellDistSweeps sweeps (even, so the result lands back in cell_dist)
+    const int grid2 = grid_for(n_cells, 256);
+    for (int it = 0; it < kCellDistSweeps; it += 2) {
+        cell_dist_relax_kernel<<<grid2, 256, 0, stream>>>(cell_dist, cell_scratch, vol.ncell[0], vol.ncell[1], vol.ncell[2]);
+        cell_dist_relax_kernel<<<grid2, 256, 0, stream>>>(cell_scratch, cell_dist, vol.ncell[0], vol.ncell[1], vol.ncell[2]);
+    }
     return cudaGetLastError();
 }
 

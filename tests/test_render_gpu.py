@@ -159,7 +159,7 @@ def test_non_cubic_volume():
     want, _, counters = oracle.render(vol, *args)
     got, stats = _render_gpu(vol, *args, strict=True)
     assert image_metrics(got, want)["max_abs"] <= 1 and abs(stats["samples"] - counters["samples"]) <= 16
-    for layout in ("linear", "brick", "linear_swz", "brick_swz"):
+    for layout in ("linear", "swizzle"):
         os.environ["PYVR_CUDA_LAYOUT"] = layout
         try:
             got, _ = _render_gpu(vol, *args)
@@ -179,7 +179,7 @@ def test_lut_sizes(size):
     assert_parity(got, want)
 
 
-@pytest.mark.parametrize("layout", ["linear", "brick", "linear_swz", "brick_swz"])
+@pytest.mark.parametrize("layout", ["linear", "swizzle"])
 def test_half_texels_within_tolerance(c1, layout):
     vol, light, lut = c1
     cam, cfg = Camera.isometric_view(distance=3.0), RenderConfig.balanced()
@@ -192,7 +192,7 @@ def test_half_texels_within_tolerance(c1, layout):
     assert_parity(got, want)
 
 
-@pytest.mark.parametrize("layout", ["linear", "brick", "linear_swz", "brick_swz"])
+@pytest.mark.parametrize("layout", ["swizzle"])
 def test_layouts_are_bit_identical(c1, layout):
     """The texel layout only moves bytes around: every layout must give the same float image."""
     vol, light, lut = c1
