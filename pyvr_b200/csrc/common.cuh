@@ -33,10 +33,11 @@ struct VolumeDesc {
     float bmin[3], bmax[3];
     // fast path: voxel coordinate = world * vscale + voff  (= tc * n - 0.5)
     float vscale[3], voff[3];
-    // empty-space skipping: one byte per 8^3 macrocell = chessboard distance (in cells, capped) to the
-    // nearest cell in which some sample may have alpha != 0 (0 = this cell is active), and the bounding
-    // box of the active cells {lo_x, lo_y, lo_z, hi_x, hi_y, hi_z} in cell units (hi inclusive; lo > hi
-    // when no cell is active).  Both are written by launch_cell_classify.
+    // empty-space skipping: one byte per 8^3 macrocell (a cell is "active" if some sample in it may have
+    // alpha != 0): b < 128 = inactive and every cell within chessboard radius b-1 is inactive; b >= 128 =
+    // active and every cell within radius b-128 is active.  Plus the bounding box of the active cells
+    // {lo_x, lo_y, lo_z, hi_x, hi_y, hi_z} in cell units (hi inclusive; lo > hi when no cell is active).
+    // Both are written by launch_cell_classify.
     const uint8_t *cell_dist;
     const int *active_box;
     int ncell[3];
@@ -75,7 +76,8 @@ cudaError_t launch_pack_texels(const float *scalar, const float *normals, const 
                                bool half_texels, cudaStream_t stream);
 cudaError_t launch_cell_minmax(const VolumeDesc &vol, bool half_texels, float2 *cell_minmax,
                                cudaStream_t stream);
-constexpr int kCellDistSweeps = 16;   // distance values above this are only lower bounds (still safe)
+constexpr int kCellDistCap = 15;      // distances saturate here (a nibble); a saturated value is a lower bound
+constexpr int kCellDistSweeps = 14;   // relaxation sweeps: every distance <= 14 is exact
 cudaError_t launch_cell_classify(const float2 *cell_minmax, const VolumeDesc &vol, const float4 *lut,
                                  int lut_size, uint8_t *cell_dist, uint8_t *cell_scratch, int *active_box,
                                  cudaStream_t stream);

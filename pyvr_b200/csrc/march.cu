@@ -45,10 +45,9 @@ __device__ __forceinline__ Taps axis_taps(float u, int n) {
 
 // Same, from a voxel-space coordinate already known to lie in [-0.5, n-0.5].
 __device__ __forceinline__ Taps voxel_taps(float x, int n) {
-    float fl = floorf(x);
+    const int i = __float2int_rd(x);   // F2I.FLOOR; the fraction comes from I2FP, not a second round-trip
     Taps t;
-    t.f = x - fl;
-    int i = (int)fl;
+    t.f = x - (float)i;
     t.i0 = max(i, 0);
     t.i1 = min(i + 1, n - 1);
     return t;
@@ -176,6 +175,12 @@ march_kernel(const __grid_constant__ MarchArgs a) {
     unsigned n_samples = 0, n_fetched = 0;
     bool hit = false, terminated = false;
 
+    // State of the fast march.  It lives outside the set-up conditionals because the fast loop is
+    // warp-synchronous: all 32 lanes stay in it (idle lanes predicated off) until the whole warp is done.
+    float X0 = 0.0f, Y0 = 0.0f, Z0 = 0.0f, DX = 0.0f, DY = 0.0f, DZ = 0.0f;
+    int i = 0, i_lo = 0, j_hi = -1, last = -1;
+    bool alive = false;
+
     if (in_image && vol.texels != nullptr && a.lut_size > 0) {
         // ---- ray set-up: the oracle's arithmetic in BOTH modes.  The first sample sits exactly on the
         // box surface, so whether it passes the validity test is decided by the last bit of these
@@ -221,8 +226,8 @@ march_kernel(const __grid_constant__ MarchArgs a) {
 
             if (STRICT) {
                 float pxw = p0x, pyw = p0y, pzw = p0z;
-                int i = 0;
-                for (; i < n_steps && acc.a < a.term_alpha; ++i) {
+                int k = 0;
+                for (; k < n_steps && acc.a < a.term_alpha; ++k) {
                     const float tcx = (pxw - vol.bmin[0]) / (vol.bmax[0] - vol.bmin[0]);
                     const float tcy = (pyw - vol.bmin[1]) / (vol.bmax[1] - vol.bmin[1]);
                     const float tcz = (pzw - vol.bmin[2]) / (vol.bmax[2] - vol.bmin[2]);
@@ -230,12 +235,12 @@ march_kernel(const __grid_constant__ MarchArgs a) {
                         ++n_samples; ++n_fetched;
                         const Taps tx = axis_taps(tcx, vol.n[0]), ty = axis_taps(tcy, vol.n[1]),
                                    tz = axis_taps(tcz, vol.n[2]);
-                        const Corner8 k = gather<HALF, IDX>(vol, tx, ty, tz);
-                        shade<true>(a, s_lut, k, tx.f, ty.f, tz.f, acc);
+                        const Corner8 c8 = gather<HALF, IDX>(vol, tx, ty, tz);
+                        shade<true>(a, s_lut, c8, tx.f, ty.f, tz.f, acc);
                     }
                     pxw += sx; pyw += sy; pzw += sz;
                 }
-                terminated = (i < n_steps) || (n_steps < a.max_steps && acc.a >= a.term_alpha);
+                terminated = (k < n_steps) || (n_steps < a.max_steps && acc.a >= a.term_alpha);
             } else {
                 // ---- voxel-space lattice x(i) = X0 + i*DX; sample i is valid iff -0.5 <= x <= n-0.5 on
                 // every axis, except sample 0 (on the box surface), which takes the reference's own test.
@@ -243,15 +248,17 @@ march_kernel(const __grid_constant__ MarchArgs a) {
                 const float t0y = (p0y - vol.bmin[1]) / (vol.bmax[1] - vol.bmin[1]);
                 const float t0z = (p0z - vol.bmin[2]) / (vol.bmax[2] - vol.bmin[2]);
                 const bool valid0 = t0x >= 0.0f && t0x <= 1.0f && t0y >= 0.0f && t0y <= 1.0f && t0z >= 0.0f && t0z <= 1.0f;
-                const float X0 = fmaf(p0x, vol.vscale[0], vol.voff[0]), DX = sx * vol.vscale[0];
-                const float Y0 = fmaf(p0y, vol.vscale[1], vol.voff[1]), DY = sy * vol.vscale[1];
-                const float Z0 = fmaf(p0z, vol.vscale[2], vol.voff[2]), DZ = sz * vol.vscale[2];
                 const float hx = (float)vol.n[0] - 0.5f, hy = (float)vol.n[1] - 0.5f, hz = (float)vol.n[2] - 0.5f;
-                auto valid = [&](int i) -> bool {
-                    if (i <= 0) return i == 0 && valid0;
-                    if (i >= n_steps) return false;
-                    const float fi = (float)i;
-                    const float x = fmaf(fi, DX, X0), y = fmaf(fi, DY, Y0), z = fmaf(fi, DZ, Z0);
+                // The entry point lies on the box surface up to round-off (~1e-5 voxel): pull it inside so
+                // that the taps of sample 0 stay in the array.
+                X0 = fminf(fmaxf(fmaf(p0x, vol.vscale[0], vol.voff[0]), -0.5f), hx); DX = sx * vol.vscale[0];
+                Y0 = fminf(fmaxf(fmaf(p0y, vol.vscale[1], vol.voff[1]), -0.5f), hy); DY = sy * vol.vscale[1];
+                Z0 = fminf(fmaxf(fmaf(p0z, vol.vscale[2], vol.voff[2]), -0.5f), hz); DZ = sz * vol.vscale[2];
+                auto valid = [&](int k) -> bool {
+                    if (k <= 0) return k == 0 && valid0;
+                    if (k >= n_steps) return false;
+                    const float fk = (float)k;
+                    const float x = fmaf(fk, DX, X0), y = fmaf(fk, DY, Y0), z = fmaf(fk, DZ, Z0);
                     return x >= -0.5f && x <= hx && y >= -0.5f && y <= hy && z >= -0.5f && z <= hz;
                 };
 
@@ -260,7 +267,7 @@ march_kernel(const __grid_constant__ MarchArgs a) {
                 index_slab(X0, DX, -0.5f, hx, enter, exit);
                 index_slab(Y0, DY, -0.5f, hy, enter, exit);
                 index_slab(Z0, DZ, -0.5f, hz, enter, exit);
-                int i_lo = (int)fminf(fmaxf(ceilf(enter), 0.0f), (float)n_steps);
+                i_lo = (int)fminf(fmaxf(ceilf(enter), 0.0f), (float)n_steps);
                 int i_hi = (int)fminf(fmaxf(floorf(exit), -1.0f), (float)(n_steps - 1));
                 if (valid(i_lo - 1)) --i_lo; else if (!valid(i_lo)) ++i_lo;
                 if (valid(i_hi + 1)) ++i_hi; else if (!valid(i_hi)) --i_hi;
@@ -268,9 +275,9 @@ march_kernel(const __grid_constant__ MarchArgs a) {
                 else if (i_lo == 0) i_lo = 1;
 
                 // clip to the bounding box of the active macrocells (samples outside add exactly zero)
-                const bool ess = (a.flags & PYVR_FLAG_ESS) && vol.cell_dist != nullptr;
-                int j_lo = i_lo, j_hi = i_hi;
-                if (ess) {
+                int j_lo = i_lo;
+                j_hi = i_hi;
+                if ((a.flags & PYVR_FLAG_ESS) && vol.cell_dist != nullptr) {
                     const int *ab = vol.active_box;
                     const int cx0 = __ldg(ab + 0), cy0 = __ldg(ab + 1), cz0 = __ldg(ab + 2);
                     const int cx1 = __ldg(ab + 3), cy1 = __ldg(ab + 4), cz1 = __ldg(ab + 5);
@@ -285,51 +292,70 @@ march_kernel(const __grid_constant__ MarchArgs a) {
                         j_hi = min(j_hi, (int)fminf(fmaxf(ceilf(exi) + 1.0f, -1.0f), (float)n_steps));
                     }
                 }
-
-                const float rDX = 1.0f / DX, rDY = 1.0f / DY, rDZ = 1.0f / DZ;
-                int i = j_lo, last = i_hi;        // `last` = index of the last sample the reference executes
-                int cell_end = ess ? j_lo : 0x7fffffff;   // first index not known to be in an active cell
-                while (true) {
-                    // phase 1: advance this ray to its next sample in an active cell
-                    Taps tx, ty, tz;
-                    bool have = false;
-                    while (i <= j_hi) {
-                        const float fi = (float)i;
-                        float x = fmaf(fi, DX, X0), y = fmaf(fi, DY, Y0), z = fmaf(fi, DZ, Z0);
-                        if (i == 0) {   // valid by the reference's test; keep the taps inside the array
-                            x = fminf(fmaxf(x, -0.5f), hx); y = fminf(fmaxf(y, -0.5f), hy); z = fminf(fmaxf(z, -0.5f), hz);
-                        }
-                        tx = voxel_taps(x, vol.n[0]); ty = voxel_taps(y, vol.n[1]); tz = voxel_taps(z, vol.n[2]);
-                        if (i < cell_end) { have = true; break; }
-                        const int cx = tx.i0 >> 3, cy = ty.i0 >> 3, cz = tz.i0 >> 3;
-                        // d = 0: active cell.  d > 0: every cell within chessboard radius d-1 is inactive, so
-                        // the ray may run to the faces of that cube of cells.  Either way: whole steps that
-                        // stay inside (and inside the volume) on every axis, conservative by 0.01 step; a
-                        // zero direction component never exits.
-                        const int d = __ldg(vol.cell_dist + ((size_t)cx * vol.ncell[1] + cy) * vol.ncell[2] + cz);
-                        const int r = max(d - 1, 0);
-                        const float ex = ((DX > 0.0f ? fminf((float)(8 * (cx + r) + 8), hx) : fmaxf((float)(8 * (cx - r)), -0.5f)) - x) * rDX;
-                        const float ey = ((DY > 0.0f ? fminf((float)(8 * (cy + r) + 8), hy) : fmaxf((float)(8 * (cy - r)), -0.5f)) - y) * rDY;
-                        const float ez = ((DZ > 0.0f ? fminf((float)(8 * (cz + r) + 8), hz) : fmaxf((float)(8 * (cz - r)), -0.5f)) - z) * rDZ;
-                        const float tmin = fminf(fminf(DX != 0.0f ? ex : 3.0e38f, DY != 0.0f ? ey : 3.0e38f),
-                                                 DZ != 0.0f ? ez : 3.0e38f);
-                        const int stay = max((int)fminf(floorf(tmin - 0.01f), 1.0e6f), 1);
-                        const bool active = d == 0;
-                        if (active) { cell_end = i + stay; have = true; break; }
-                        i += stay;
-                    }
-                    if (!have) break;
-                    // phase 2: every lane still here has a sample to fetch
-                    ++n_fetched;
-                    const Corner8 k = gather<HALF, IDX>(vol, tx, ty, tz);
-                    shade<false>(a, s_lut, k, tx.f, ty.f, tz.f, acc);
-                    if (acc.a >= a.term_alpha) { terminated = true; last = i; break; }
-                    ++i;
-                }
-                n_samples = (unsigned)max(last - i_lo + 1, 0);
-                if (terminated && last + 1 >= a.max_steps) terminated = false;
+                i = j_lo;
+                last = i_hi;        // index of the last sample the reference executes
+                alive = j_lo <= j_hi;
             }
         }
+    }
+
+    if constexpr (!STRICT) {
+        // ---- fast march, warp-synchronous.  Every round has two phases:
+        //   1. each live lane advances to its next sample that lies in an active macrocell (per-lane
+        //      loop over the cell map; lanes still inside a known active run pass straight through);
+        //   2. after a warp vote -- which also reconverges the lanes -- all lanes that have a sample
+        //      fetch and shade it together.
+        // The vote matters: without it the compiler lets the lanes that came out of the cell lookup and
+        // the lanes that skipped it run phase 2 as two separate half-empty groups (measured: 17 of 32
+        // lanes active in the gather).
+        const bool ess = (a.flags & PYVR_FLAG_ESS) && vol.cell_dist != nullptr;
+        const float hx = (float)vol.n[0] - 0.5f, hy = (float)vol.n[1] - 0.5f, hz = (float)vol.n[2] - 0.5f;
+        const float rDX = 1.0f / DX, rDY = 1.0f / DY, rDZ = 1.0f / DZ;
+        const int max_last = a.max_steps - 1;
+        int run_end = ess ? i : 0x7fffffff;   // first index not known to lie in an active run of cells
+        while (true) {
+            Taps tx, ty, tz;
+            bool have = false;
+            if (alive) {
+                while (i <= j_hi) {
+                    const float fi = (float)i;
+                    const float x = fmaf(fi, DX, X0), y = fmaf(fi, DY, Y0), z = fmaf(fi, DZ, Z0);
+                    tx = voxel_taps(x, vol.n[0]); ty = voxel_taps(y, vol.n[1]); tz = voxel_taps(z, vol.n[2]);
+                    if (i < run_end) { have = true; break; }
+                    // Cell byte (volume_pack.cu): b < 128: inactive, every cell within chessboard radius
+                    // b-1 is inactive too; b >= 128: active, every cell within radius b-128 is active.
+                    // Either way the ray may run to the faces of that cube of cells: whole steps that stay
+                    // inside it (and inside the volume) on every axis, conservative by 0.01 step; a zero
+                    // direction component never exits.
+                    const int cx = tx.i0 >> 3, cy = ty.i0 >> 3, cz = tz.i0 >> 3;
+                    const int b = __ldg(vol.cell_dist + (cx * vol.ncell[1] + cy) * vol.ncell[2] + cz);
+                    const bool active = b >= 128;
+                    const int r = active ? b - 128 : b - 1;
+                    const float ex = ((DX > 0.0f ? fminf((float)(8 * (cx + r) + 8), hx) : fmaxf((float)(8 * (cx - r)), -0.5f)) - x) * rDX;
+                    const float ey = ((DY > 0.0f ? fminf((float)(8 * (cy + r) + 8), hy) : fmaxf((float)(8 * (cy - r)), -0.5f)) - y) * rDY;
+                    const float ez = ((DZ > 0.0f ? fminf((float)(8 * (cz + r) + 8), hz) : fmaxf((float)(8 * (cz - r)), -0.5f)) - z) * rDZ;
+                    const float tmin = fminf(fminf(DX != 0.0f ? ex : 3.0e38f, DY != 0.0f ? ey : 3.0e38f),
+                                             DZ != 0.0f ? ez : 3.0e38f);
+                    const int stay = max((int)fminf(floorf(tmin - 0.01f), 1.0e6f), 1);
+                    if (active) { run_end = i + stay; have = true; break; }
+                    i += stay;
+                }
+                alive = have;
+            }
+            if (!__any_sync(0xffffffffu, have)) break;
+            if (have) {
+                ++n_fetched;
+                const Corner8 c8 = gather<HALF, IDX>(vol, tx, ty, tz);
+                shade<false>(a, s_lut, c8, tx.f, ty.f, tz.f, acc);
+                if (acc.a >= a.term_alpha) {
+                    terminated = i < max_last;
+                    last = i;
+                    alive = false;
+                }
+                ++i;
+            }
+        }
+        if (hit) n_samples = (unsigned)max(last - i_lo + 1, 0);
     }
 
     // fragment colour -> [0,1] clamp -> blend onto the (0,0,0,0) clear -> clamp -> round to RGBA8

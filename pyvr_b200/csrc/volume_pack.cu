@@ -6,8 +6,9 @@
 //    A Volume without normals is packed with normal = (s, 0, 0): that is what the shader samples when
 //    `normal_volume` is left on texture unit 0 (renderer.py:143-146).
 //  * cell_minmax / cell_classify / cell_dist_relax: the macrocell grid for exact empty-space skipping.
-//    A cell is inactive only if every sample whose lower taps fall in it provably has alpha_tf == 0;
-//    inactive cells then get their chessboard distance to the nearest active cell.
+//    A cell is inactive only if every sample whose lower taps fall in it provably has alpha_tf == 0.
+//    Every cell then gets the chessboard radius of the largest cube of like cells around it, so the march
+//    crosses empty space AND solid interiors with one map lookup per cube instead of one per cell.
 #include "common.cuh"
 
 namespace pyvr {
@@ -115,7 +116,9 @@ cell_classify_kernel(const float2 *__restrict__ mm, VolumeDesc v, const float4 *
         const int jl = (int)fminf(fmaxf(xl, 0.0f), size - 1.0f);   // NaN/-inf -> 0, +inf -> size-1
         const int jh = (int)fminf(fmaxf(xh, 0.0f), size - 1.0f);
         const bool on = (s_nonzero_before[jh + 1] - s_nonzero_before[jl]) != 0;
-        active[c] = on ? 0 : 255;   // seed of the distance map: 0 = active, 255 = "far"
+        // seeds of the two distance maps, one per nibble: low = distance to the nearest active cell,
+        // high = distance to the nearest inactive cell (0 = "is one", kCellDistCap = "far")
+        active[c] = on ? (uint8_t)(kCellDistCap << 4) : (uint8_t)kCellDistCap;
         if (on) {   // bounding box of the active cells, block-local first
             const int cz = (int)(c % v.ncell[2]);
             const size_t rest = c / v.ncell[2];
@@ -129,10 +132,10 @@ cell_classify_kernel(const float2 *__restrict__ mm, VolumeDesc v, const float4 *
     else if (threadIdx.x < 6) atomicMax(active_box + threadIdx.x, s_box[threadIdx.x]);
 }
 
-// One relaxation sweep of the chessboard (Chebyshev) distance to the nearest active cell, in cells,
-// capped at 255: out = min(in, 1 + min over the 26 neighbours).  After k sweeps every value <= k is
-// final.  A cell with distance d > 0 guarantees that all cells within Chebyshev radius d-1 are inactive,
-// so a ray inside it may jump to the faces of that (2d-1)^3 cube of cells in one step.
+// One relaxation sweep of both chessboard (Chebyshev) distance maps, in cells: each nibble becomes
+// min(itself, 1 + min over the 26 neighbours).  Seeds are 0, everything else starts at kCellDistCap; after
+// k <= kCellDistCap - 1 sweeps every value <= k is exact and the rest still hold kCellDistCap, which is then
+// a valid LOWER bound of their true distance.  Cells outside the grid are neither active nor inactive.
 __global__ void __launch_bounds__(256)
 cell_dist_relax_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, int n0, int n1, int n2) {
     const long long total = (long long)n0 * n1 * n2;
@@ -141,25 +144,38 @@ cell_dist_relax_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out
         const int cz = (int)(c % n2);
         const long long rest = c / n2;
         const int cy = (int)(rest % n1), cx = (int)(rest / n1);
-        int best = in[c];
-        if (best > 0) {
-            int nb = 255;
-            for (int dx = -1; dx <= 1; ++dx) {
-                const int x = cx + dx;
-                if (x < 0 || x >= n0) continue;
-                for (int dy = -1; dy <= 1; ++dy) {
-                    const int y = cy + dy;
-                    if (y < 0 || y >= n1) continue;
-                    for (int dz = -1; dz <= 1; ++dz) {
-                        const int z = cz + dz;
-                        if (z < 0 || z >= n2) continue;
-                        nb = min(nb, (int)in[((long long)x * n1 + y) * n2 + z]);
-                    }
+        const int self = in[c];
+        int lo = kCellDistCap, hi = kCellDistCap;
+        for (int dx = -1; dx <= 1; ++dx) {
+            const int x = cx + dx;
+            if (x < 0 || x >= n0) continue;
+            for (int dy = -1; dy <= 1; ++dy) {
+                const int y = cy + dy;
+                if (y < 0 || y >= n1) continue;
+                for (int dz = -1; dz <= 1; ++dz) {
+                    const int z = cz + dz;
+                    if (z < 0 || z >= n2) continue;
+                    const int nb = in[((long long)x * n1 + y) * n2 + z];
+                    lo = min(lo, nb & 15);
+                    hi = min(hi, nb >> 4);
                 }
             }
-            best = min(best, nb + 1);
         }
-        out[c] = (uint8_t)min(best, 255);
+        lo = min(self & 15, min(lo + 1, kCellDistCap));
+        hi = min(self >> 4, min(hi + 1, kCellDistCap));
+        out[c] = (uint8_t)((hi << 4) | lo);
+    }
+}
+
+// Nibble pair -> the byte the march reads (march.cu, phase 1):
+//   inactive cell:  d      (1 .. cap)      every cell within chessboard radius d-1 is inactive
+//   active cell:    128+w  (w = 0 .. cap-1) every cell within chessboard radius w is active
+__global__ void __launch_bounds__(256)
+cell_dist_finish_kernel(uint8_t *__restrict__ cells, long long total) {
+    for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < total;
+         c += (long long)gridDim.x * blockDim.x) {
+        const int v = cells[c], lo = v & 15, hi = v >> 4;
+        cells[c] = lo == 0 ? (uint8_t)(128 + hi - 1) : (uint8_t)lo;
     }
 }
 
@@ -206,12 +222,14 @@ cudaError_t launch_cell_classify(const float2 *cell_minmax, const VolumeDesc &vo
     }
     reset_active_box_kernel<<<1, 32, 0, stream>>>(active_box);
     cell_classify_kernel<<<grid, 256, smem, stream>>>(cell_minmax, vol, lut, lut_size, cell_dist, active_box);
-    // distance map: kCellDistSweeps sweeps (even, so the result lands back in cell_dist)
+    // distance maps: kCellDistSweeps sweeps (even, so the result lands back in cell_dist), then the final byte
     const int grid2 = grid_for(n_cells, 256);
+    static_assert(kCellDistSweeps % 2 == 0 && kCellDistSweeps < kCellDistCap && kCellDistCap <= 15, "nibble-sized distances");
     for (int it = 0; it < kCellDistSweeps; it += 2) {
         cell_dist_relax_kernel<<<grid2, 256, 0, stream>>>(cell_dist, cell_scratch, vol.ncell[0], vol.ncell[1], vol.ncell[2]);
         cell_dist_relax_kernel<<<grid2, 256, 0, stream>>>(cell_scratch, cell_dist, vol.ncell[0], vol.ncell[1], vol.ncell[2]);
     }
+    cell_dist_finish_kernel<<<grid2, 256, 0, stream>>>(cell_dist, n_cells);
     return cudaGetLastError();
 }
 

@@ -5,12 +5,11 @@ TAG=${1:-r01}
 OUT=gpurun_out
 mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/${TAG}_gpu.txt
+nproc >> $OUT/${TAG}_gpu.txt
 timeout 1200 python -m pytest tests -m gpu -q 2>&1 | tail -40 > $OUT/${TAG}_pytest.txt
 tail -15 $OUT/${TAG}_pytest.txt
-for variant in "" "--no-ess" "--layout linear" "--layout linear --no-ess" "--texels f16" "--texels f16 --no-ess"; do
-  name=$(echo "bench$variant" | tr -d ' -')
-  timeout 600 python bench.py --steps 3 --warmup 3 --views-per-step 6 --skip-cpu-baseline $variant > $OUT/${TAG}_${name}.json 2> $OUT/${TAG}_${name}.err
-  python - "$OUT/${TAG}_${name}.json" "$variant" <<'PY'
+summ() {
+  python - "$1" "$2" <<'PY'
 import json, sys
 try:
     d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
@@ -18,16 +17,26 @@ try:
     print(f"{sys.argv[2] or 'default':28s} value={d['value']:.1f} Gs/s  fps={d['frames_per_s']:.1f}  e2e={d['e2e']['value']:.1f}  "
           f"kernel_ms/launch={r['kernel_ms_per_launch']:.2f}  fetched/ref={r['samples_fetched_per_launch']/r['samples_reference_per_launch']:.3f}  frac={r['frac']:.2f}")
 except Exception as e:
-    print(sys.argv[2], "FAILED", e)
+    print(sys.argv[2], "FAILED", e, open(sys.argv[1].replace('.json','.err')).read()[-800:])
 PY
+}
+# the driver's own command lines first
+timeout 900 python bench.py > $OUT/${TAG}_bench_default.json 2> $OUT/${TAG}_bench_default.err; summ $OUT/${TAG}_bench_default.json "driver default"
+timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/${TAG}_bench_reference.json 2> $OUT/${TAG}_bench_reference.err; tail -c 600 $OUT/${TAG}_bench_reference.json
+for variant in "--no-ess" "--layout linear --no-ess" "--texels f16" "--texels f16 --no-ess"; do
+  name=$(echo "bench$variant" | tr -d ' -')
+  timeout 600 python bench.py --steps 3 --warmup 3 --views-per-step 6 --skip-cpu-baseline $variant > $OUT/${TAG}_${name}.json 2> $OUT/${TAG}_${name}.err
+  summ $OUT/${TAG}_${name}.json "$variant"
 done
 # ncu: launch list of a short default run, then one full capture of the march kernel
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/${TAG}_launches.csv \
-    python bench.py --steps 2 --warmup 1 --views-per-step 2 --skip-cpu-baseline > $OUT/${TAG}_ncu_launch.log 2>&1
+    python bench.py --steps 2 --warmup 3 --views-per-step 12 --skip-cpu-baseline > $OUT/${TAG}_ncu_launch.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:march_kernel -s 1 -c 1 -f -o $OUT/${TAG}_march \
     python bench.py --steps 1 --warmup 1 --views-per-step 1 --skip-cpu-baseline > $OUT/${TAG}_ncu_full.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:march_kernel -s 1 -c 1 -f -o $OUT/${TAG}_march_noess \
     python bench.py --steps 1 --warmup 1 --views-per-step 1 --skip-cpu-baseline --no-ess > $OUT/${TAG}_ncu_full_noess.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:march_kernel -s 1 -c 1 -f -o $OUT/${TAG}_march_f16_noess \
+    python bench.py --steps 1 --warmup 1 --views-per-step 1 --skip-cpu-baseline --no-ess --texels f16 > $OUT/${TAG}_ncu_full_f16_noess.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:normals -c 1 -f -o $OUT/${TAG}_normals \
     python bench.py --steps 1 --warmup 1 --views-per-step 1 --skip-cpu-baseline > $OUT/${TAG}_ncu_normals.log 2>&1
 ls -la $OUT | tail -30
