@@ -24,7 +24,8 @@
 extern "C" {
 #endif
 
-#define PYVR_CUDA_ABI_VERSION 1
+#define PYVR_CUDA_ABI_VERSION 2
+#define PYVR_IPC_HANDLE_BYTES 64   /* sizeof(cudaIpcMemHandle_t) */
 
 typedef enum {
     PYVR_OK = 0,
@@ -110,6 +111,24 @@ int pyvr_cuda_upload_volume(pyvr_ctx *ctx, const float *scalar, const float *nor
                             const float bmin[3], const float bmax[3],
                             int texel_format, int src_is_device);
 
+/* Sort-last brick (no reference counterpart; SURVEY.md section 8 e, config C5): this context holds the
+ * sub-block [origin, origin + local_dims) of a volume of global_dims texels and renders only the samples
+ * whose voxel coordinate lies in [own_lo, own_hi) on every axis (the volume's outer faces are open-ended),
+ * on the sample lattice of the WHOLE volume, so the partial images of all bricks composite to the
+ * single-GPU result.  All index triples are in world order (x, y, z) = numpy axes (0, 1, 2) of
+ * data[ix, iy, iz] (z memory-fastest); bmin/bmax are the bounds of the whole volume.  The sub-block must
+ * include texel own_hi on every axis where own_hi < global_dims (the +1 ghost layer the upper trilinear
+ * taps reach).  scalar/normals: local_dims[0]*local_dims[1]*local_dims[2] (x3) floats. */
+int pyvr_cuda_upload_brick(pyvr_ctx *ctx, const float *scalar, const float *normals,
+                           const int local_dims[3], const int global_dims[3], const int origin[3],
+                           const int own_lo[3], const int own_hi[3],
+                           const float bmin[3], const float bmax[3], int texel_format, int src_is_device);
+
+/* Image-space sharding (SURVEY.md section 8 e, config C4): this context marches the 64x64-pixel tile
+ * groups g with g % count == rank and writes zeros elsewhere, so the frames of all ranks add up
+ * (e.g. ncclReduce SUM over uint8) to the full frame, bit for bit.  count = 1 restores normal rendering. */
+int pyvr_cuda_set_pixel_shard(pyvr_ctx *ctx, int rank, int count);
+
 /* --- create_rgba_transfer_function_texture (manager.py:137-186): (size,4) RGBA binary32 ---------- */
 int pyvr_cuda_set_lut(pyvr_ctx *ctx, const float *rgba, int size);
 
@@ -135,6 +154,12 @@ int pyvr_cuda_render_batch(pyvr_ctx *ctx, const pyvr_view *views, int n, uint8_t
 /* The fragment colour BEFORE blending/quantisation, width*height*4 floats (acc_rgb, acc_a). */
 int pyvr_cuda_render_accum(pyvr_ctx *ctx, float *out, int out_is_device);
 
+/* Sort-last relay (exact): continue the accumulation `in_accum` (device, width*height*4 floats, the
+ * fragment colours of the bricks IN FRONT of this context's brick; NULL = nothing in front) through this
+ * brick and write the result to `out_accum` (device; may alias in_accum).  Passing the image through the
+ * bricks in visibility order reproduces the single-GPU march operation for operation, stop rule included. */
+int pyvr_cuda_render_accum_relay(pyvr_ctx *ctx, const float *in_accum, float *out_accum);
+
 int pyvr_cuda_get_stats(pyvr_ctx *ctx, pyvr_stats *out);
 
 /* --- compute_normal_volume (pyvr/datasets/synthetic.py:109-122) ----------------------------------
@@ -142,6 +167,28 @@ int pyvr_cuda_get_stats(pyvr_ctx *ctx, pyvr_stats *out);
  * pointers on `device`.  kernel_ms (may be NULL) receives the stencil kernel's device time. */
 int pyvr_cuda_compute_normals(int device, const float *in, float *out, int n0, int n1, int n2,
                               int buffers_are_device, float *kernel_ms);
+
+/* --- sort-last compositing (no reference counterpart) ----------------------------------------------
+ * Partial images are the pre-blend fragment colours pyvr_cuda_render_accum produces: n_pixels * 4 floats
+ * (premultiplied rgb, alpha), all DEVICE pointers here.  `back` may be a peer-mapped pointer
+ * (pyvr_cuda_ipc_open): the merge then reads it across NVLink.  cuda_stream: a cudaStream_t or NULL. */
+/* out = front over back; a front pixel at or above termination_alpha hides the back pixel (the shader's
+ * stop rule, volume.frag.glsl:87, at brick granularity).  out may alias front. */
+int pyvr_cuda_composite_over(int device, const float *front, const float *back, float *out, size_t n_pixels,
+                             float termination_alpha, void *cuda_stream);
+/* Blend onto the cleared target + RGBA8 quantisation of a composited image (manager.py:217-220, 29). */
+int pyvr_cuda_finalize_rgba8(int device, const float *accum, uint8_t *out, size_t n_pixels, uint32_t flags,
+                             void *cuda_stream);
+/* Plain cudaMalloc memory (IPC-exportable, unlike a sub-allocation of a framework's caching pool). */
+int pyvr_cuda_device_alloc(int device, size_t bytes, void **out);
+int pyvr_cuda_device_free(int device, void *ptr);
+/* CUDA IPC: share a pyvr_cuda_device_alloc buffer with the other single-GPU processes of the node. */
+int pyvr_cuda_ipc_export(int device, void *ptr, uint8_t handle[PYVR_IPC_HANDLE_BYTES]);
+int pyvr_cuda_ipc_open(int device, const uint8_t handle[PYVR_IPC_HANDLE_BYTES], void **out);
+int pyvr_cuda_ipc_close(int device, void *ptr);
+/* Synchronous copy; kind: 1 = host->device, 2 = device->host, 3 = device->device (peer pointers allowed). */
+int pyvr_cuda_memcpy(int device, void *dst, const void *src, size_t bytes, int kind, void *cuda_stream);
+int pyvr_cuda_stream_synchronize(int device, void *cuda_stream);
 
 /* --- misc ------------------------------------------------------------------------------------------ */
 /* Tuning knobs (no reference counterpart).  "swizzle": 1 (default) = L1 bank swizzle of the packed texel

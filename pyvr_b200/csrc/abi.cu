@@ -67,6 +67,7 @@ struct pyvr_ctx {
     int *active_box = nullptr;     // 6 ints, see VolumeDesc
     size_t n_cells = 0;
     bool swizzle = true;  // L1 bank swizzle of the texel layout (common.cuh); off only for A/B profiling
+    int shard_rank = 0, shard_count = 1;   // image-space tile sharding (pyvr_cuda_set_pixel_shard)
 
     // transfer function
     float4 *lut = nullptr;
@@ -153,16 +154,22 @@ void inverse4_f32(const float *m, float *o) {
     o[15] = (a20 * b03 - a21 * b01 + a22 * b00) * id;
 }
 
-void fill_volume_desc(pyvr_ctx *c, int shape0, int shape1, int shape2, const float bmin[3], const float bmax[3]) {
+// local[3] = stored texel counts along world x, y, z; global/org/own_* = NULL for a whole volume.
+void fill_volume_desc(pyvr_ctx *c, const int local[3], const int global[3], const int org[3],
+                      const int own_lo[3], const int own_hi[3], const float bmin[3], const float bmax[3]) {
     VolumeDesc &v = c->vol;
-    // GL (width, height, depth) = (shape0, shape1, shape2); width is the memory-fastest axis and is
-    // addressed by tex_coord.x = world z after the shader's swizzle (volume.frag.glsl:90).
-    v.n[0] = shape2; v.n[1] = shape1; v.n[2] = shape0;
+    v.bricked = global != nullptr;
     for (int a = 0; a < 3; ++a) {
+        v.n[a] = local[a];
+        v.gn[a] = global ? global[a] : local[a];
+        v.org[a] = org ? org[a] : 0;
+        // ownership in voxel coordinates; the volume's outer faces are open-ended
+        v.own_lo[a] = (own_lo && own_lo[a] > 0) ? (float)own_lo[a] : -3.0e38f;
+        v.own_hi[a] = (own_hi && own_hi[a] < v.gn[a]) ? (float)own_hi[a] : 3.0e38f;
         v.bmin[a] = bmin[a]; v.bmax[a] = bmax[a];
         const double ext = (double)bmax[a] - (double)bmin[a];
-        v.vscale[a] = (float)((double)v.n[a] / ext);
-        v.voff[a] = (float)(-(double)bmin[a] * (double)v.n[a] / ext - 0.5);
+        v.vscale[a] = (float)((double)v.gn[a] / ext);
+        v.voff[a] = (float)(-(double)bmin[a] * (double)v.gn[a] / ext - 0.5);
         v.ncell[a] = (v.n[a] + 7) / 8;
     }
     // lines of SLOTS consecutive-z texels with an optional slot rotation; see common.cuh
@@ -236,15 +243,19 @@ MarchArgs make_args(const pyvr_ctx *c) {
     a.term_alpha = p.termination_alpha;
     a.flags = p.flags;
     a.counters = c->d_counters;
+    a.shard_rank = c->shard_rank;
+    a.shard_count = c->shard_count;
     return a;
 }
 
 // Launch the march for `n` views already resident in c->d_views[first..], timed with events.
-int march(pyvr_ctx *c, int first, int n, uchar4 *out8, float4 *out_acc, size_t ev_pair) {
+int march(pyvr_ctx *c, int first, int n, uchar4 *out8, float4 *out_acc, size_t ev_pair,
+          const float4 *in_acc = nullptr) {
     MarchArgs a = make_args(c);
     a.views = c->d_views + first;
     a.out8 = out8;
     a.out_acc = out_acc;
+    a.in_acc = in_acc;
     CU(cudaEventRecord(c->ev[2 * ev_pair], c->stream));
     CU(launch_march(a, n, c->half_texels, c->texel_bytes / (c->half_texels ? 8 : 16) >= ((size_t)1 << 31), c->stream));
     CU(cudaEventRecord(c->ev[2 * ev_pair + 1], c->stream));
@@ -367,26 +378,18 @@ int pyvr_cuda_set_option(pyvr_ctx *c, const char *key, int value) {
     return fail(PYVR_ERR_INVALID, "unknown option '%s'", key);
 }
 
-int pyvr_cuda_upload_volume(pyvr_ctx *c, const float *scalar, const float *normals, int shape0, int shape1,
-                            int shape2, const float bmin[3], const float bmax[3], int texel_format,
-                            int src_is_device) {
-    if (!c || !scalar || !bmin || !bmax) return fail(PYVR_ERR_INVALID, "NULL argument");
-    if (shape0 <= 0 || shape1 <= 0 || shape2 <= 0)
-        return fail(PYVR_ERR_INVALID, "Volume data must be 3D with positive extents, got (%d, %d, %d)", shape0, shape1, shape2);
-    if (texel_format != PYVR_TEXEL_F32X4 && texel_format != PYVR_TEXEL_F16X4)
-        return fail(PYVR_ERR_INVALID, "unknown texel format %d", texel_format);
-    for (int a = 0; a < 3; ++a)
-        if (!(bmax[a] > bmin[a])) return fail(PYVR_ERR_INVALID, "max_bounds must be greater than min_bounds");
-    DeviceGuard guard(c->device);
-    CU(cudaStreamSynchronize(c->stream));
-    free_volume(c);  // the reference leaks the previous textures (manager.py:232-236); not replicated
+}  // extern "C" (reopened below)
 
-    c->half_texels = texel_format == PYVR_TEXEL_F16X4;
-    fill_volume_desc(c, shape0, shape1, shape2, bmin, bmax);
-    const size_t voxels = (size_t)shape0 * shape1 * shape2;
+namespace {
+
+// Shared tail of upload_volume / upload_brick: allocate, stage, pack, build the macrocell grid.
+// c->vol (dims, ownership, bounds) and c->half_texels are already set.
+int upload_packed(pyvr_ctx *c, const float *scalar, const float *normals, int src_is_device) {
+    const VolumeDesc &v = c->vol;
+    const size_t voxels = (size_t)v.n[0] * v.n[1] * v.n[2];
     const size_t n_tex = texel_count(c);
     c->texel_bytes = n_tex * (c->half_texels ? 8 : 16);
-    c->n_cells = (size_t)c->vol.ncell[0] * c->vol.ncell[1] * c->vol.ncell[2];
+    c->n_cells = (size_t)v.ncell[0] * v.ncell[1] * v.ncell[2];
     CU(cudaMalloc(&c->texels, c->texel_bytes));
     CU(cudaMalloc(&c->cell_minmax, c->n_cells * sizeof(float2)));
     CU(cudaMalloc(&c->cell_dist, c->n_cells));
@@ -418,6 +421,68 @@ int pyvr_cuda_upload_volume(pyvr_ctx *c, const float *scalar, const float *norma
     CU(e);
     c->have_volume = true;
     return classify_cells(c);
+}
+
+}  // namespace
+
+extern "C" {
+
+int pyvr_cuda_upload_volume(pyvr_ctx *c, const float *scalar, const float *normals, int shape0, int shape1,
+                            int shape2, const float bmin[3], const float bmax[3], int texel_format,
+                            int src_is_device) {
+    if (!c || !scalar || !bmin || !bmax) return fail(PYVR_ERR_INVALID, "NULL argument");
+    if (shape0 <= 0 || shape1 <= 0 || shape2 <= 0)
+        return fail(PYVR_ERR_INVALID, "Volume data must be 3D with positive extents, got (%d, %d, %d)", shape0, shape1, shape2);
+    if (texel_format != PYVR_TEXEL_F32X4 && texel_format != PYVR_TEXEL_F16X4)
+        return fail(PYVR_ERR_INVALID, "unknown texel format %d", texel_format);
+    for (int a = 0; a < 3; ++a)
+        if (!(bmax[a] > bmin[a])) return fail(PYVR_ERR_INVALID, "max_bounds must be greater than min_bounds");
+    DeviceGuard guard(c->device);
+    CU(cudaStreamSynchronize(c->stream));
+    free_volume(c);  // the reference leaks the previous textures (manager.py:232-236); not replicated
+
+    c->half_texels = texel_format == PYVR_TEXEL_F16X4;
+    // GL (width, height, depth) = (shape0, shape1, shape2); width is the memory-fastest axis and is
+    // addressed by tex_coord.x = world z after the shader's swizzle (volume.frag.glsl:90).
+    const int local[3] = {shape2, shape1, shape0};
+    fill_volume_desc(c, local, nullptr, nullptr, nullptr, nullptr, bmin, bmax);
+    return upload_packed(c, scalar, normals, src_is_device);
+}
+
+int pyvr_cuda_upload_brick(pyvr_ctx *c, const float *scalar, const float *normals, const int local_dims[3],
+                           const int global_dims[3], const int origin[3], const int own_lo[3],
+                           const int own_hi[3], const float bmin[3], const float bmax[3], int texel_format,
+                           int src_is_device) {
+    if (!c || !scalar || !local_dims || !global_dims || !origin || !own_lo || !own_hi || !bmin || !bmax)
+        return fail(PYVR_ERR_INVALID, "NULL argument");
+    if (texel_format != PYVR_TEXEL_F32X4 && texel_format != PYVR_TEXEL_F16X4)
+        return fail(PYVR_ERR_INVALID, "unknown texel format %d", texel_format);
+    for (int a = 0; a < 3; ++a) {
+        if (!(bmax[a] > bmin[a])) return fail(PYVR_ERR_INVALID, "max_bounds must be greater than min_bounds");
+        if (local_dims[a] <= 0 || global_dims[a] <= 0 || origin[a] < 0 || origin[a] + local_dims[a] > global_dims[a])
+            return fail(PYVR_ERR_INVALID, "brick [%d, %d) does not fit axis %d of extent %d", origin[a],
+                        origin[a] + local_dims[a], a, global_dims[a]);
+        if (own_lo[a] < origin[a] || own_hi[a] <= own_lo[a] || own_hi[a] > global_dims[a])
+            return fail(PYVR_ERR_INVALID, "ownership [%d, %d) on axis %d is outside the brick", own_lo[a], own_hi[a], a);
+        // samples with x in [own_hi - 1, own_hi) read texel own_hi: it must be stored unless it is clamped away
+        const int need_hi = own_hi[a] < global_dims[a] ? own_hi[a] : global_dims[a] - 1;
+        if (need_hi > origin[a] + local_dims[a] - 1)
+            return fail(PYVR_ERR_INVALID, "brick lacks the +1 ghost layer on axis %d", a);
+    }
+    DeviceGuard guard(c->device);
+    CU(cudaStreamSynchronize(c->stream));
+    free_volume(c);
+    c->half_texels = texel_format == PYVR_TEXEL_F16X4;
+    fill_volume_desc(c, local_dims, global_dims, origin, own_lo, own_hi, bmin, bmax);
+    return upload_packed(c, scalar, normals, src_is_device);
+}
+
+int pyvr_cuda_set_pixel_shard(pyvr_ctx *c, int rank, int count) {
+    if (!c) return fail(PYVR_ERR_INVALID, "ctx is NULL");
+    if (count < 1 || rank < 0 || rank >= count) return fail(PYVR_ERR_INVALID, "shard %d of %d", rank, count);
+    c->shard_rank = rank;
+    c->shard_count = count;
+    return PYVR_OK;
 }
 
 int pyvr_cuda_set_lut(pyvr_ctx *c, const float *rgba, int size) {
@@ -590,6 +655,22 @@ int pyvr_cuda_render_accum(pyvr_ctx *c, float *out, int out_is_device) {
     return finish_stats(c, 1, 1);
 }
 
+int pyvr_cuda_render_accum_relay(pyvr_ctx *c, const float *in_accum, float *out_accum) {
+    if (!c || !out_accum) return fail(PYVR_ERR_INVALID, "NULL argument");
+    if (!renderable(c) || !c->have_view) return fail(PYVR_ERR_STATE, "relay rendering needs a volume, a LUT and a camera");
+    if (c->params.flags & PYVR_FLAG_STRICT) return fail(PYVR_ERR_STATE, "relay rendering is a fast-path feature");
+    DeviceGuard guard(c->device);
+    memset(&c->stats, 0, sizeof c->stats);
+    int rc = ensure_views(c, 1);
+    if (rc == PYVR_OK) rc = ensure_events(c, 1);
+    if (rc != PYVR_OK) return rc;
+    CU(cudaMemcpyAsync(c->d_views, &c->view, sizeof(pyvr_view), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemsetAsync(c->d_counters, 0, sizeof(unsigned long long) * CNT_N, c->stream));
+    rc = march(c, 0, 1, nullptr, reinterpret_cast<float4 *>(out_accum), 0, reinterpret_cast<const float4 *>(in_accum));
+    if (rc != PYVR_OK) return rc;
+    return finish_stats(c, 1, 1);
+}
+
 int pyvr_cuda_get_stats(pyvr_ctx *c, pyvr_stats *out) {
     if (!c || !out) return fail(PYVR_ERR_INVALID, "NULL argument");
     *out = c->stats;
@@ -641,6 +722,78 @@ int pyvr_cuda_host_alloc(size_t bytes, void **out) {
 
 int pyvr_cuda_host_free(void *p) {
     if (p) CU(cudaFreeHost(p));
+    return PYVR_OK;
+}
+
+int pyvr_cuda_composite_over(int device, const float *front, const float *back, float *out, size_t n_pixels,
+                             float termination_alpha, void *cuda_stream) {
+    if (!front || !back || !out) return fail(PYVR_ERR_INVALID, "NULL argument");
+    DeviceGuard guard(device);
+    CU(launch_composite_over(reinterpret_cast<const float4 *>(front), reinterpret_cast<const float4 *>(back),
+                             reinterpret_cast<float4 *>(out), n_pixels, termination_alpha, (cudaStream_t)cuda_stream));
+    return PYVR_OK;
+}
+
+int pyvr_cuda_finalize_rgba8(int device, const float *accum, uint8_t *out, size_t n_pixels, uint32_t flags,
+                             void *cuda_stream) {
+    if (!accum || !out) return fail(PYVR_ERR_INVALID, "NULL argument");
+    DeviceGuard guard(device);
+    CU(launch_finalize_rgba8(reinterpret_cast<const float4 *>(accum), reinterpret_cast<uchar4 *>(out), n_pixels,
+                             flags, (cudaStream_t)cuda_stream));
+    return PYVR_OK;
+}
+
+int pyvr_cuda_device_alloc(int device, size_t bytes, void **out) {
+    if (!out) return fail(PYVR_ERR_INVALID, "out is NULL");
+    DeviceGuard guard(device);
+    CU(cudaMalloc(out, bytes));
+    return PYVR_OK;
+}
+
+int pyvr_cuda_device_free(int device, void *ptr) {
+    DeviceGuard guard(device);
+    if (ptr) CU(cudaFree(ptr));
+    return PYVR_OK;
+}
+
+int pyvr_cuda_ipc_export(int device, void *ptr, uint8_t handle[PYVR_IPC_HANDLE_BYTES]) {
+    if (!ptr || !handle) return fail(PYVR_ERR_INVALID, "NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == PYVR_IPC_HANDLE_BYTES, "IPC handle size");
+    DeviceGuard guard(device);
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, ptr));
+    memcpy(handle, &h, sizeof h);
+    return PYVR_OK;
+}
+
+int pyvr_cuda_ipc_open(int device, const uint8_t handle[PYVR_IPC_HANDLE_BYTES], void **out) {
+    if (!handle || !out) return fail(PYVR_ERR_INVALID, "NULL argument");
+    DeviceGuard guard(device);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof h);
+    CU(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+    return PYVR_OK;
+}
+
+int pyvr_cuda_ipc_close(int device, void *ptr) {
+    DeviceGuard guard(device);
+    if (ptr) CU(cudaIpcCloseMemHandle(ptr));
+    return PYVR_OK;
+}
+
+int pyvr_cuda_memcpy(int device, void *dst, const void *src, size_t bytes, int kind, void *cuda_stream) {
+    if (!dst || !src) return fail(PYVR_ERR_INVALID, "NULL argument");
+    if (kind < 1 || kind > 3) return fail(PYVR_ERR_INVALID, "kind must be 1 (H2D), 2 (D2H) or 3 (D2D)");
+    DeviceGuard guard(device);
+    const cudaMemcpyKind k = kind == 1 ? cudaMemcpyHostToDevice : kind == 2 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    CU(cudaMemcpyAsync(dst, src, bytes, k, (cudaStream_t)cuda_stream));
+    CU(cudaStreamSynchronize((cudaStream_t)cuda_stream));
+    return PYVR_OK;
+}
+
+int pyvr_cuda_stream_synchronize(int device, void *cuda_stream) {
+    DeviceGuard guard(device);
+    CU(cudaStreamSynchronize((cudaStream_t)cuda_stream));
     return PYVR_OK;
 }
 

@@ -25,8 +25,16 @@ namespace pyvr {
 // l1tex data pipe at 99 %).  With it they spread over the banks ("L1 bank swizzle").
 struct VolumeDesc {
     const void *texels;   // float4 {s,nx,ny,nz} or 4 x half
-    int n[3];             // texel counts along world x, y, z.  NB world z is the memory-fastest axis
-                          // of the array the reference uploads: (nz, ny, nx) = numpy shape (0, 1, 2).
+    int n[3];             // texel counts of the STORED array along world x, y, z.  NB world z is the
+                          // memory-fastest axis of the array the reference uploads: (nz, ny, nx) = numpy
+                          // shape (0, 1, 2).
+    // Sort-last bricks (pyvr_cuda_upload_brick): the stored array is the sub-block [org, org + n) of a
+    // volume of gn texels; this brick owns the samples whose voxel coordinate x satisfies
+    // own_lo <= x < own_hi on every axis (own_lo = -inf / own_hi = +inf on the volume's outer faces).
+    // For a whole volume gn = n, org = 0, bricked = 0.
+    int gn[3], org[3];
+    float own_lo[3], own_hi[3];
+    int bricked;
     int slot_shift;       // log2(SLOTS): 3 for f32x4, 4 for f16x4
     int row_lines;        // lines per z-row = ceil(n[2] / SLOTS)
     int swz_x, swz_y;     // slot rotation multipliers (0, 0 = no swizzle)
@@ -64,14 +72,40 @@ struct MarchArgs {
     unsigned flags;
     uchar4 *out8;                  // n_views * height * width, row 0 = bottom; may be null
     float4 *out_acc;               // same shape, pre-blend fragment colour; may be null
+    const float4 *in_acc;          // relay (sort-last, exact): fragment colour accumulated by the bricks in
+                                   // front of this one; the march continues from it.  May be null / == out_acc.
     unsigned long long *counters;  // [samples, fetched, rays_hit, rays_terminated]
+    // Image-space sharding (multi-GPU tiles): 64x64-pixel tile groups are dealt round-robin; this launch
+    // marches the groups with (group index) % shard_count == shard_rank and writes zeros elsewhere, so the
+    // per-rank frames add up to the full frame.  shard_count <= 1: everything.
+    int shard_rank, shard_count;
 };
+
+// Fragment colour -> what fbo.read returns: clamp to [0,1], blend SRC_ALPHA / ONE_MINUS_SRC_ALPHA onto the
+// (0,0,0,0) clear (manager.py:217-220; skipped with PYVR_FLAG_NO_BLEND), clamp, round to nearest RGBA8.
+__device__ __forceinline__ uchar4 fragment_to_rgba8(float cr, float cg, float cb, float ca, unsigned flags) {
+    auto clamp01 = [](float v) { return fminf(fmaxf(v, 0.0f), 1.0f); };
+    const float al = clamp01(ca);
+    float r = clamp01(cr), g = clamp01(cg), b = clamp01(cb), o = al;
+    if (!(flags & PYVR_FLAG_NO_BLEND)) { r *= al; g *= al; b *= al; o = al * al; }
+    uchar4 q;
+    q.x = (unsigned char)__float2uint_rn(clamp01(r) * 255.0f);
+    q.y = (unsigned char)__float2uint_rn(clamp01(g) * 255.0f);
+    q.z = (unsigned char)__float2uint_rn(clamp01(b) * 255.0f);
+    q.w = (unsigned char)__float2uint_rn(clamp01(o) * 255.0f);
+    return q;
+}
 
 enum { CNT_SAMPLES = 0, CNT_FETCHED = 1, CNT_HIT = 2, CNT_TERM = 3, CNT_N = 4 };
 
 // Launchers (defined next to their kernels).
 cudaError_t launch_march(const MarchArgs &args, int n_views, bool half_texels, bool wide_index,
                          cudaStream_t stream);
+// composite.cu: sort-last compositing of pre-blend fragment colours (premultiplied rgb, alpha)
+cudaError_t launch_composite_over(const float4 *front, const float4 *back, float4 *out, size_t n_pixels,
+                                  float term_alpha, cudaStream_t stream);
+cudaError_t launch_finalize_rgba8(const float4 *accum, uchar4 *out, size_t n_pixels, unsigned flags,
+                                  cudaStream_t stream);
 cudaError_t launch_pack_texels(const float *scalar, const float *normals, const VolumeDesc &vol,
                                bool half_texels, cudaStream_t stream);
 cudaError_t launch_cell_minmax(const VolumeDesc &vol, bool half_texels, float2 *cell_minmax,

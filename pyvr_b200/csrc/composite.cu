@@ -1,0 +1,76 @@
+// composite.cu -- sort-last compositing of partial images (sm_100a).
+//
+// No reference counterpart: the reference renders one volume on one device.  When the volume is split
+// into bricks across GPUs (SURVEY.md section 8 e, config C5), every GPU marches its brick on the GLOBAL
+// sample lattice and produces the pre-blend fragment colour of its samples alone -- premultiplied rgb and
+// alpha, exactly what volume.frag.glsl:112-115 accumulates.  Front-to-back accumulation is associative:
+//     acc(front ++ back) = acc(front) + (1 - acc_a(front)) * acc(back),
+// so partial images are merged with `over` in visibility order (binary swap across ranks,
+// pyvr_b200/multi_gpu.py), and only the final image goes through the blend + RGBA8 quantisation of
+// manager.py:217-220,29 (fragment_to_rgba8, shared with the march epilogue).
+//
+// The shader stops a ray once accumulated alpha reaches 0.99 (volume.frag.glsl:87).  Each brick applies
+// that rule to its own segment (it cannot see the alpha accumulated in front of it); `over` applies it
+// again at brick granularity: a front image at or above the threshold hides the back image, and when the
+// merge would cross the threshold -- the reference stops somewhere INSIDE the back brick -- only the
+// fraction s of the back image that brings alpha to the threshold is added (first-order model: colour and
+// alpha of the back segment grow in proportion).  The reference ends such a ray within one sample's
+// contribution above 0.99, so saturating pixels agree to about one RGBA8 level (measured by the tests;
+// without the clip it is up to 5).  The relay mode (pyvr_b200/multi_gpu.py) is exact when that matters.
+//
+// HBM/NVLink-bound streaming kernels: 32 algorithmic bytes read + 16 written per pixel for `over`
+// (`back` may be a peer-mapped pointer: the load then crosses NVLink and the merge overlaps the transfer),
+// 16 read + 4 written for finalize.  One float4 per thread, fully coalesced.
+#include "common.cuh"
+
+namespace pyvr {
+namespace {
+
+__global__ void __launch_bounds__(256)
+composite_over_kernel(const float4 *__restrict__ front, const float4 *__restrict__ back,
+                      float4 *__restrict__ out, size_t n, float term_alpha) {
+    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (size_t)gridDim.x * blockDim.x) {
+        float4 f = front[p];
+        if (f.w < term_alpha) {
+            // streaming load: a peer buffer is read exactly once
+            const float4 b = __ldcs(back + p);
+            float t = 1.0f - f.w;
+            if (fmaf(t, b.w, f.w) > term_alpha) t = (term_alpha - f.w) / b.w;   // s * (1 - f.w), s < 1; b.w > 0 here
+            f.x = fmaf(t, b.x, f.x);
+            f.y = fmaf(t, b.y, f.y);
+            f.z = fmaf(t, b.z, f.z);
+            f.w = fmaf(t, b.w, f.w);
+        }
+        out[p] = f;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+finalize_rgba8_kernel(const float4 *__restrict__ accum, uchar4 *__restrict__ out, size_t n, unsigned flags) {
+    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (size_t)gridDim.x * blockDim.x) {
+        const float4 c = accum[p];
+        out[p] = fragment_to_rgba8(c.x, c.y, c.z, c.w, flags);
+    }
+}
+
+inline int stream_grid(size_t n) {
+    size_t g = (n + 255) / 256;
+    const size_t cap = 148 * 8;
+    return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace
+
+cudaError_t launch_composite_over(const float4 *front, const float4 *back, float4 *out, size_t n_pixels,
+                                  float term_alpha, cudaStream_t stream) {
+    composite_over_kernel<<<stream_grid(n_pixels), 256, 0, stream>>>(front, back, out, n_pixels, term_alpha);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_finalize_rgba8(const float4 *accum, uchar4 *out, size_t n_pixels, unsigned flags,
+                                  cudaStream_t stream) {
+    finalize_rgba8_kernel<<<stream_grid(n_pixels), 256, 0, stream>>>(accum, out, n_pixels, flags);
+    return cudaGetLastError();
+}
+
+}  // namespace pyvr

@@ -73,25 +73,29 @@ struct Corner8 {
 
 // Eight corner fetches from the line/slot layout of common.cuh.  IDX is int (packed array < 2^31
 // texels) or long long.
-template <bool HALF, typename IDX>
+template <bool HALF, typename IDX, bool BRICK>
 __device__ __forceinline__ Corner8 gather(const VolumeDesc &v, const Taps &tx, const Taps &ty, const Taps &tz) {
     constexpr int LS = HALF ? 4 : 3, SLOT_MASK = (1 << LS) - 1;
-    const IDX rx0 = (IDX)tx.i0 * v.n[1], rx1 = (IDX)tx.i1 * v.n[1];
-    const IDX l00 = (rx0 + ty.i0) * v.row_lines, l01 = (rx0 + ty.i1) * v.row_lines;
-    const IDX l10 = (rx1 + ty.i0) * v.row_lines, l11 = (rx1 + ty.i1) * v.row_lines;
-    const int lz0 = tz.i0 >> LS, lz1 = tz.i1 >> LS;
-    const int sx0 = v.swz_x * tx.i0, sx1 = v.swz_x * tx.i1, sy0 = v.swz_y * ty.i0, sy1 = v.swz_y * ty.i1;
+    // taps are indices of the whole volume; a brick stores the sub-block that starts at v.org
+    const int x0 = BRICK ? tx.i0 - v.org[0] : tx.i0, x1 = BRICK ? tx.i1 - v.org[0] : tx.i1;
+    const int y0 = BRICK ? ty.i0 - v.org[1] : ty.i0, y1 = BRICK ? ty.i1 - v.org[1] : ty.i1;
+    const int z0 = BRICK ? tz.i0 - v.org[2] : tz.i0, z1 = BRICK ? tz.i1 - v.org[2] : tz.i1;
+    const IDX rx0 = (IDX)x0 * v.n[1], rx1 = (IDX)x1 * v.n[1];
+    const IDX l00 = (rx0 + y0) * v.row_lines, l01 = (rx0 + y1) * v.row_lines;
+    const IDX l10 = (rx1 + y0) * v.row_lines, l11 = (rx1 + y1) * v.row_lines;
+    const int lz0 = z0 >> LS, lz1 = z1 >> LS;
+    const int sx0 = v.swz_x * x0, sx1 = v.swz_x * x1, sy0 = v.swz_y * y0, sy1 = v.swz_y * y1;
     const int s00 = sx0 + sy0, s01 = sx0 + sy1, s10 = sx1 + sy0, s11 = sx1 + sy1;
 #define PYVR_AT(l, s, lz, iz) ((((l) + (lz)) << LS) + (IDX)(((s) + (iz)) & SLOT_MASK))
     Corner8 r;
-    r.c[0] = load_texel<HALF, IDX>(v.texels, PYVR_AT(l00, s00, lz0, tz.i0));
-    r.c[1] = load_texel<HALF, IDX>(v.texels, PYVR_AT(l00, s00, lz1, tz.i1));
-    r.c[2] = load_texel<HALF, IDX>(v.texels, PYVR_AT(l01, s01, lz0, tz.i0));
-    r.c[3] = load_texel<HALF, IDX>(v.texels, PYVR_AT(l01, s01, lz1, tz.i1));
-    r.c[4] = load_texel<HALF, IDX>(v.texels, PYVR_AT(l10, s10, lz0, tz.i0));
-    r.c[5] = load_texel<HALF, IDX>(v.texels, PYVR_AT(l10, s10, lz1, tz.i1));
-    r.c[6] = load_texel<HALF, IDX>(v.texels, PYVR_AT(l11, s11, lz0, tz.i0));
-    r.c[7] = load_texel<HALF, IDX>(v.texels, PYVR_AT(l11, s11, lz1, tz.i1));
+    r.c[0] = load_texel<HALF, IDX>(v.texels, PYVR_AT(l00, s00, lz0, z0));
+    r.c[1] = load_texel<HALF, IDX>(v.texels, PYVR_AT(l00, s00, lz1, z1));
+    r.c[2] = load_texel<HALF, IDX>(v.texels, PYVR_AT(l01, s01, lz0, z0));
+    r.c[3] = load_texel<HALF, IDX>(v.texels, PYVR_AT(l01, s01, lz1, z1));
+    r.c[4] = load_texel<HALF, IDX>(v.texels, PYVR_AT(l10, s10, lz0, z0));
+    r.c[5] = load_texel<HALF, IDX>(v.texels, PYVR_AT(l10, s10, lz1, z1));
+    r.c[6] = load_texel<HALF, IDX>(v.texels, PYVR_AT(l11, s11, lz0, z0));
+    r.c[7] = load_texel<HALF, IDX>(v.texels, PYVR_AT(l11, s11, lz1, z1));
 #undef PYVR_AT
     return r;
 }
@@ -100,8 +104,6 @@ __device__ __forceinline__ Corner8 gather(const VolumeDesc &v, const Taps &tx, c
 #define PYVR_TRILERP(field)                                                                       \
     lerpf(lerpf(lerpf(k.c[0].field, k.c[1].field, wz), lerpf(k.c[2].field, k.c[3].field, wz), wy), \
           lerpf(lerpf(k.c[4].field, k.c[5].field, wz), lerpf(k.c[6].field, k.c[7].field, wz), wy), wx)
-
-__device__ __forceinline__ float clamp01(float v) { return fminf(fmaxf(v, 0.0f), 1.0f); }
 
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
@@ -157,17 +159,32 @@ __device__ __forceinline__ void index_slab(float X0, float D, float lo, float hi
     }
 }
 
-template <bool STRICT, bool HALF, typename IDX>
+template <bool STRICT, bool HALF, typename IDX, bool BRICK>
 __global__ void __launch_bounds__(CTA_THREADS)
 march_kernel(const __grid_constant__ MarchArgs a) {
-    extern __shared__ float4 s_lut[];
-    for (int i = threadIdx.x; i < a.lut_size; i += CTA_THREADS) s_lut[i] = a.lut[i];
-    __syncthreads();
-
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int px = blockIdx.x * TILE_W + (warp & 1) * 8 + (lane & 7);
     const int py = blockIdx.y * TILE_H + (warp >> 1) * 4 + (lane >> 3);
     const bool in_image = px < a.width && py < a.height;
+
+    // image-space sharding: a CTA whose 64x64 tile group belongs to another rank only clears its pixels
+    if (a.shard_count > 1) {
+        const int gx = (blockIdx.x * TILE_W) >> 6, gy = (blockIdx.y * TILE_H) >> 6;
+        const int groups_x = (a.width + 63) >> 6;
+        if ((gy * (groups_x + 1) + gx) % a.shard_count != a.shard_rank) {   // +1: skew the rows of groups
+            if (in_image) {
+                const size_t pix = ((size_t)blockIdx.z * a.height + py) * a.width + px;
+                const float4 keep = a.in_acc ? a.in_acc[pix] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                if (a.out_acc) a.out_acc[pix] = keep;
+                if (a.out8) a.out8[pix] = a.in_acc ? fragment_to_rgba8(keep.x, keep.y, keep.z, keep.w, a.flags) : make_uchar4(0, 0, 0, 0);
+            }
+            return;
+        }
+    }
+
+    extern __shared__ float4 s_lut[];
+    for (int i = threadIdx.x; i < a.lut_size; i += CTA_THREADS) s_lut[i] = a.lut[i];
+    __syncthreads();
     const pyvr_view &vw = a.views[blockIdx.z];
     const VolumeDesc &vol = a.vol;
 
@@ -233,9 +250,9 @@ march_kernel(const __grid_constant__ MarchArgs a) {
                     const float tcz = (pzw - vol.bmin[2]) / (vol.bmax[2] - vol.bmin[2]);
                     if (tcx >= 0.0f && tcx <= 1.0f && tcy >= 0.0f && tcy <= 1.0f && tcz >= 0.0f && tcz <= 1.0f) {
                         ++n_samples; ++n_fetched;
-                        const Taps tx = axis_taps(tcx, vol.n[0]), ty = axis_taps(tcy, vol.n[1]),
-                                   tz = axis_taps(tcz, vol.n[2]);
-                        const Corner8 c8 = gather<HALF, IDX>(vol, tx, ty, tz);
+                        const Taps tx = axis_taps(tcx, vol.gn[0]), ty = axis_taps(tcy, vol.gn[1]),
+                                   tz = axis_taps(tcz, vol.gn[2]);
+                        const Corner8 c8 = gather<HALF, IDX, false>(vol, tx, ty, tz);
                         shade<true>(a, s_lut, c8, tx.f, ty.f, tz.f, acc);
                     }
                     pxw += sx; pyw += sy; pzw += sz;
@@ -248,7 +265,7 @@ march_kernel(const __grid_constant__ MarchArgs a) {
                 const float t0y = (p0y - vol.bmin[1]) / (vol.bmax[1] - vol.bmin[1]);
                 const float t0z = (p0z - vol.bmin[2]) / (vol.bmax[2] - vol.bmin[2]);
                 const bool valid0 = t0x >= 0.0f && t0x <= 1.0f && t0y >= 0.0f && t0y <= 1.0f && t0z >= 0.0f && t0z <= 1.0f;
-                const float hx = (float)vol.n[0] - 0.5f, hy = (float)vol.n[1] - 0.5f, hz = (float)vol.n[2] - 0.5f;
+                const float hx = (float)vol.gn[0] - 0.5f, hy = (float)vol.gn[1] - 0.5f, hz = (float)vol.gn[2] - 0.5f;
                 // The entry point lies on the box surface up to round-off (~1e-5 voxel): pull it inside so
                 // that the taps of sample 0 stay in the array.
                 X0 = fminf(fmaxf(fmaf(p0x, vol.vscale[0], vol.voff[0]), -0.5f), hx); DX = sx * vol.vscale[0];
@@ -274,6 +291,30 @@ march_kernel(const __grid_constant__ MarchArgs a) {
                 if (valid0) i_lo = 0;
                 else if (i_lo == 0) i_lo = 1;
 
+                if (BRICK) {
+                    // Sort-last brick: keep the samples this brick owns.  Ownership is a convex box in voxel
+                    // space, so the owned indices form one interval; the slab estimate is corrected with the
+                    // ownership predicate itself, evaluated on the very x(k) every brick computes, so each
+                    // sample of the ray ends up in exactly one brick.
+                    auto owned = [&](int k) -> bool {
+                        const float fk = (float)k;
+                        const float x = fmaf(fk, DX, X0), y = fmaf(fk, DY, Y0), z = fmaf(fk, DZ, Z0);
+                        return x >= vol.own_lo[0] && x < vol.own_hi[0] && y >= vol.own_lo[1] && y < vol.own_hi[1] &&
+                               z >= vol.own_lo[2] && z < vol.own_hi[2];
+                    };
+                    float en = -3.0e38f, exi = 3.0e38f;
+                    index_slab(X0, DX, vol.own_lo[0], vol.own_hi[0], en, exi);
+                    index_slab(Y0, DY, vol.own_lo[1], vol.own_hi[1], en, exi);
+                    index_slab(Z0, DZ, vol.own_lo[2], vol.own_hi[2], en, exi);
+                    int o_lo = max(i_lo, (int)fminf(fmaxf(ceilf(en) - 2.0f, 0.0f), 2.0e9f));
+                    int o_hi = min(i_hi, (int)fminf(fmaxf(floorf(exi) + 2.0f, -1.0f), 2.0e9f));
+                    for (int g = 0; g < 6 && o_lo <= o_hi && !owned(o_lo); ++g) ++o_lo;
+                    for (int g = 0; g < 6 && o_lo <= o_hi && !owned(o_hi); ++g) --o_hi;
+                    if (o_lo <= o_hi && !(owned(o_lo) && owned(o_hi))) o_hi = o_lo - 1;   // grazing ray
+                    i_lo = o_lo;
+                    i_hi = o_hi;
+                }
+
                 // clip to the bounding box of the active macrocells (samples outside add exactly zero)
                 int j_lo = i_lo;
                 j_hi = i_hi;
@@ -285,9 +326,10 @@ march_kernel(const __grid_constant__ MarchArgs a) {
                         j_hi = j_lo - 1;
                     } else {
                         float en = -3.0e38f, exi = 3.0e38f;
-                        index_slab(X0, DX, cx0 == 0 ? -0.5f : (float)(8 * cx0), fminf((float)(8 * cx1 + 8), hx), en, exi);
-                        index_slab(Y0, DY, cy0 == 0 ? -0.5f : (float)(8 * cy0), fminf((float)(8 * cy1 + 8), hy), en, exi);
-                        index_slab(Z0, DZ, cz0 == 0 ? -0.5f : (float)(8 * cz0), fminf((float)(8 * cz1 + 8), hz), en, exi);
+                        const int fx0 = vol.org[0] + 8 * cx0, fy0 = vol.org[1] + 8 * cy0, fz0 = vol.org[2] + 8 * cz0;
+                        index_slab(X0, DX, fx0 == 0 ? -0.5f : (float)fx0, fminf((float)(vol.org[0] + 8 * cx1 + 8), hx), en, exi);
+                        index_slab(Y0, DY, fy0 == 0 ? -0.5f : (float)fy0, fminf((float)(vol.org[1] + 8 * cy1 + 8), hy), en, exi);
+                        index_slab(Z0, DZ, fz0 == 0 ? -0.5f : (float)fz0, fminf((float)(vol.org[2] + 8 * cz1 + 8), hz), en, exi);
                         j_lo = max(j_lo, (int)fminf(fmaxf(floorf(en) - 1.0f, 0.0f), (float)n_steps));
                         j_hi = min(j_hi, (int)fminf(fmaxf(ceilf(exi) + 1.0f, -1.0f), (float)n_steps));
                     }
@@ -300,6 +342,13 @@ march_kernel(const __grid_constant__ MarchArgs a) {
     }
 
     if constexpr (!STRICT) {
+        // relay: continue the accumulation of the bricks in front.  A ray that arrives saturated executes no
+        // sample here, exactly as the single pass would not (volume.frag.glsl:87 tests before each sample).
+        if (a.in_acc != nullptr && in_image) {
+            const float4 in = a.in_acc[((size_t)blockIdx.z * a.height + py) * a.width + px];
+            acc.r = in.x; acc.g = in.y; acc.b = in.z; acc.a = in.w;
+            if (acc.a >= a.term_alpha) { alive = false; last = i_lo - 1; }
+        }
         // ---- fast march, warp-synchronous.  Every round has two phases:
         //   1. each live lane advances to its next sample that lies in an active macrocell (per-lane
         //      loop over the cell map; lanes still inside a known active run pass straight through);
@@ -309,7 +358,7 @@ march_kernel(const __grid_constant__ MarchArgs a) {
         // the lanes that skipped it run phase 2 as two separate half-empty groups (measured: 17 of 32
         // lanes active in the gather).
         const bool ess = (a.flags & PYVR_FLAG_ESS) && vol.cell_dist != nullptr;
-        const float hx = (float)vol.n[0] - 0.5f, hy = (float)vol.n[1] - 0.5f, hz = (float)vol.n[2] - 0.5f;
+        const float hx = (float)vol.gn[0] - 0.5f, hy = (float)vol.gn[1] - 0.5f, hz = (float)vol.gn[2] - 0.5f;
         const float rDX = 1.0f / DX, rDY = 1.0f / DY, rDZ = 1.0f / DZ;
         const int max_last = a.max_steps - 1;
         int run_end = ess ? i : 0x7fffffff;   // first index not known to lie in an active run of cells
@@ -320,20 +369,22 @@ march_kernel(const __grid_constant__ MarchArgs a) {
                 while (i <= j_hi) {
                     const float fi = (float)i;
                     const float x = fmaf(fi, DX, X0), y = fmaf(fi, DY, Y0), z = fmaf(fi, DZ, Z0);
-                    tx = voxel_taps(x, vol.n[0]); ty = voxel_taps(y, vol.n[1]); tz = voxel_taps(z, vol.n[2]);
+                    tx = voxel_taps(x, vol.gn[0]); ty = voxel_taps(y, vol.gn[1]); tz = voxel_taps(z, vol.gn[2]);
                     if (i < run_end) { have = true; break; }
                     // Cell byte (volume_pack.cu): b < 128: inactive, every cell within chessboard radius
                     // b-1 is inactive too; b >= 128: active, every cell within radius b-128 is active.
                     // Either way the ray may run to the faces of that cube of cells: whole steps that stay
                     // inside it (and inside the volume) on every axis, conservative by 0.01 step; a zero
                     // direction component never exits.
-                    const int cx = tx.i0 >> 3, cy = ty.i0 >> 3, cz = tz.i0 >> 3;
+                    const int cx = (BRICK ? tx.i0 - vol.org[0] : tx.i0) >> 3, cy = (BRICK ? ty.i0 - vol.org[1] : ty.i0) >> 3,
+                              cz = (BRICK ? tz.i0 - vol.org[2] : tz.i0) >> 3;
                     const int b = __ldg(vol.cell_dist + (cx * vol.ncell[1] + cy) * vol.ncell[2] + cz);
                     const bool active = b >= 128;
                     const int r = active ? b - 128 : b - 1;
-                    const float ex = ((DX > 0.0f ? fminf((float)(8 * (cx + r) + 8), hx) : fmaxf((float)(8 * (cx - r)), -0.5f)) - x) * rDX;
-                    const float ey = ((DY > 0.0f ? fminf((float)(8 * (cy + r) + 8), hy) : fmaxf((float)(8 * (cy - r)), -0.5f)) - y) * rDY;
-                    const float ez = ((DZ > 0.0f ? fminf((float)(8 * (cz + r) + 8), hz) : fmaxf((float)(8 * (cz - r)), -0.5f)) - z) * rDZ;
+                    const int ox = BRICK ? vol.org[0] : 0, oy = BRICK ? vol.org[1] : 0, oz = BRICK ? vol.org[2] : 0;
+                    const float ex = ((DX > 0.0f ? fminf((float)(ox + 8 * (cx + r) + 8), hx) : fmaxf((float)(ox + 8 * (cx - r)), -0.5f)) - x) * rDX;
+                    const float ey = ((DY > 0.0f ? fminf((float)(oy + 8 * (cy + r) + 8), hy) : fmaxf((float)(oy + 8 * (cy - r)), -0.5f)) - y) * rDY;
+                    const float ez = ((DZ > 0.0f ? fminf((float)(oz + 8 * (cz + r) + 8), hz) : fmaxf((float)(oz + 8 * (cz - r)), -0.5f)) - z) * rDZ;
                     const float tmin = fminf(fminf(DX != 0.0f ? ex : 3.0e38f, DY != 0.0f ? ey : 3.0e38f),
                                              DZ != 0.0f ? ez : 3.0e38f);
                     const int stay = max((int)fminf(floorf(tmin - 0.01f), 1.0e6f), 1);
@@ -345,7 +396,7 @@ march_kernel(const __grid_constant__ MarchArgs a) {
             if (!__any_sync(0xffffffffu, have)) break;
             if (have) {
                 ++n_fetched;
-                const Corner8 c8 = gather<HALF, IDX>(vol, tx, ty, tz);
+                const Corner8 c8 = gather<HALF, IDX, BRICK>(vol, tx, ty, tz);
                 shade<false>(a, s_lut, c8, tx.f, ty.f, tz.f, acc);
                 if (acc.a >= a.term_alpha) {
                     terminated = i < max_last;
@@ -362,17 +413,7 @@ march_kernel(const __grid_constant__ MarchArgs a) {
     if (in_image) {
         const size_t pix = ((size_t)blockIdx.z * a.height + py) * a.width + px;
         if (a.out_acc) a.out_acc[pix] = make_float4(acc.r, acc.g, acc.b, acc.a);
-        if (a.out8) {
-            const float al = clamp01(acc.a);
-            float r = clamp01(acc.r), g = clamp01(acc.g), b = clamp01(acc.b), o = al;
-            if (!(a.flags & PYVR_FLAG_NO_BLEND)) { r *= al; g *= al; b *= al; o = al * al; }
-            uchar4 q;
-            q.x = (unsigned char)__float2uint_rn(clamp01(r) * 255.0f);
-            q.y = (unsigned char)__float2uint_rn(clamp01(g) * 255.0f);
-            q.z = (unsigned char)__float2uint_rn(clamp01(b) * 255.0f);
-            q.w = (unsigned char)__float2uint_rn(clamp01(o) * 255.0f);
-            a.out8[pix] = q;
-        }
+        if (a.out8) a.out8[pix] = fragment_to_rgba8(acc.r, acc.g, acc.b, acc.a, a.flags);
     }
 
     // per-warp reduction of the work counters, one atomic per counter per warp
@@ -393,10 +434,10 @@ march_kernel(const __grid_constant__ MarchArgs a) {
     }
 }
 
-template <bool STRICT, bool HALF, typename IDX>
+template <bool STRICT, bool HALF, typename IDX, bool BRICK>
 cudaError_t launch_one(const MarchArgs &a, int n_views, cudaStream_t stream) {
     const size_t smem = (size_t)a.lut_size * sizeof(float4);
-    auto kern = march_kernel<STRICT, HALF, IDX>;
+    auto kern = march_kernel<STRICT, HALF, IDX, BRICK>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -408,14 +449,20 @@ cudaError_t launch_one(const MarchArgs &a, int n_views, cudaStream_t stream) {
 
 template <bool STRICT, bool HALF>
 cudaError_t launch_idx(const MarchArgs &a, int n_views, bool wide, cudaStream_t stream) {
-    return wide ? launch_one<STRICT, HALF, long long>(a, n_views, stream)
-                : launch_one<STRICT, HALF, int>(a, n_views, stream);
+    if constexpr (!STRICT) {
+        if (a.vol.bricked)
+            return wide ? launch_one<false, HALF, long long, true>(a, n_views, stream)
+                        : launch_one<false, HALF, int, true>(a, n_views, stream);
+    }
+    return wide ? launch_one<STRICT, HALF, long long, false>(a, n_views, stream)
+                : launch_one<STRICT, HALF, int, false>(a, n_views, stream);
 }
 
 }  // namespace
 
 cudaError_t launch_march(const MarchArgs &a, int n_views, bool half_texels, bool wide_index, cudaStream_t stream) {
-    const bool strict = (a.flags & PYVR_FLAG_STRICT) != 0;
+    // bricks are marched by the fast path only (the STRICT twin of the oracle has no notion of ownership)
+    const bool strict = (a.flags & PYVR_FLAG_STRICT) != 0 && !a.vol.bricked;
     if (strict) return half_texels ? launch_idx<true, true>(a, n_views, wide_index, stream)
                                    : launch_idx<true, false>(a, n_views, wide_index, stream);
     return half_texels ? launch_idx<false, true>(a, n_views, wide_index, stream)

@@ -16,13 +16,14 @@ import numpy as np
 PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB_PATH = os.path.join(PKG_DIR, "libpyvr_cuda.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
+IPC_HANDLE_BYTES = 64
 TEXEL_F32X4, TEXEL_F16X4 = 0, 1
 FLAG_STRICT, FLAG_ESS, FLAG_NO_BLEND = 0x1, 0x2, 0x4
 
 # name -> (restype, argtypes); every symbol include/pyvr_cuda.h declares
 _c = ctypes
-_vp, _i, _fp = _c.c_void_p, _c.c_int, _c.POINTER(_c.c_float)
+_vp, _i, _fp, _ip = _c.c_void_p, _c.c_int, _c.POINTER(_c.c_float), _c.POINTER(_c.c_int)
 
 
 class View(ctypes.Structure):
@@ -58,6 +59,8 @@ SYMBOLS = {
     "pyvr_cuda_destroy": (_i, [_vp]),
     "pyvr_cuda_set_stream": (_i, [_vp, _vp]),
     "pyvr_cuda_upload_volume": (_i, [_vp, _vp, _vp, _i, _i, _i, _fp, _fp, _i, _i]),
+    "pyvr_cuda_upload_brick": (_i, [_vp, _vp, _vp, _ip, _ip, _ip, _ip, _ip, _fp, _fp, _i, _i]),
+    "pyvr_cuda_set_pixel_shard": (_i, [_vp, _i, _i]),
     "pyvr_cuda_set_lut": (_i, [_vp, _vp, _i]),
     "pyvr_cuda_set_camera": (_i, [_vp, _fp, _fp, _fp]),
     "pyvr_cuda_view_from_matrices": (_i, [_fp, _fp, _fp, _c.POINTER(View)]),
@@ -66,8 +69,18 @@ SYMBOLS = {
     "pyvr_cuda_render": (_i, [_vp, _vp, _i]),
     "pyvr_cuda_render_batch": (_i, [_vp, _vp, _i, _vp, _i]),
     "pyvr_cuda_render_accum": (_i, [_vp, _vp, _i]),
+    "pyvr_cuda_render_accum_relay": (_i, [_vp, _vp, _vp]),
     "pyvr_cuda_get_stats": (_i, [_vp, _c.POINTER(Stats)]),
     "pyvr_cuda_compute_normals": (_i, [_i, _vp, _vp, _i, _i, _i, _i, _fp]),
+    "pyvr_cuda_composite_over": (_i, [_i, _vp, _vp, _vp, _c.c_size_t, _c.c_float, _vp]),
+    "pyvr_cuda_finalize_rgba8": (_i, [_i, _vp, _vp, _c.c_size_t, _c.c_uint32, _vp]),
+    "pyvr_cuda_device_alloc": (_i, [_i, _c.c_size_t, _c.POINTER(_vp)]),
+    "pyvr_cuda_device_free": (_i, [_i, _vp]),
+    "pyvr_cuda_ipc_export": (_i, [_i, _vp, _vp]),
+    "pyvr_cuda_ipc_open": (_i, [_i, _vp, _c.POINTER(_vp)]),
+    "pyvr_cuda_ipc_close": (_i, [_i, _vp]),
+    "pyvr_cuda_memcpy": (_i, [_i, _vp, _vp, _c.c_size_t, _i, _vp]),
+    "pyvr_cuda_stream_synchronize": (_i, [_i, _vp]),
     "pyvr_cuda_set_option": (_i, [_vp, _c.c_char_p, _i]),
     "pyvr_cuda_host_alloc": (_i, [_c.c_size_t, _c.POINTER(_vp)]),
     "pyvr_cuda_host_free": (_i, [_vp]),
@@ -146,6 +159,79 @@ def compute_normals_host(volume: np.ndarray, device: int = 0, return_ms: bool = 
     check(lib().pyvr_cuda_compute_normals(device, vol.ctypes.data, out.ctypes.data,
                                           vol.shape[0], vol.shape[1], vol.shape[2], 0, _c.byref(ms)))
     return (out, ms.value) if return_ms else out
+
+
+class DeviceBuffer:
+    """Plain ``cudaMalloc`` memory (IPC-exportable).  ``ptr`` is the raw device address."""
+
+    def __init__(self, nbytes: int, device: int = 0):
+        self.device, self.nbytes = int(device), int(nbytes)
+        p = _vp()
+        check(lib().pyvr_cuda_device_alloc(self.device, max(self.nbytes, 1), _c.byref(p)))
+        self.ptr = p.value
+
+    def to_host(self, dtype=np.uint8, offset: int = 0, nbytes: Optional[int] = None) -> np.ndarray:
+        nbytes = self.nbytes - offset if nbytes is None else nbytes
+        out = np.empty(nbytes, dtype=np.uint8)
+        check(lib().pyvr_cuda_memcpy(self.device, out.ctypes.data, _vp(self.ptr + offset), nbytes, 2, None))
+        return out.view(dtype)
+
+    def from_host(self, array: np.ndarray, offset: int = 0) -> None:
+        a = np.ascontiguousarray(array)
+        check(lib().pyvr_cuda_memcpy(self.device, _vp(self.ptr + offset), a.ctypes.data, a.nbytes, 1, None))
+
+    def ipc_handle(self) -> bytes:
+        h = (_c.c_uint8 * IPC_HANDLE_BYTES)()
+        check(lib().pyvr_cuda_ipc_export(self.device, _vp(self.ptr), h))
+        return bytes(h)
+
+    def close(self) -> None:
+        if getattr(self, "ptr", None):
+            lib().pyvr_cuda_device_free(self.device, _vp(self.ptr))
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class PeerBuffer:
+    """A ``DeviceBuffer`` of another process on this node, mapped through CUDA IPC."""
+
+    def __init__(self, handle: bytes, device: int = 0):
+        self.device = int(device)
+        h = (_c.c_uint8 * IPC_HANDLE_BYTES).from_buffer_copy(handle)
+        p = _vp()
+        check(lib().pyvr_cuda_ipc_open(self.device, h, _c.byref(p)))
+        self.ptr = p.value
+
+    def close(self) -> None:
+        if getattr(self, "ptr", None):
+            lib().pyvr_cuda_ipc_close(self.device, _vp(self.ptr))
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def composite_over(device: int, front_ptr: int, back_ptr: int, out_ptr: int, n_pixels: int,
+                   termination_alpha: float = 0.99, stream: int = 0) -> None:
+    """``out = front over back`` on device pointers to ``n_pixels`` float4 pre-blend fragment colours."""
+    check(lib().pyvr_cuda_composite_over(device, _vp(front_ptr), _vp(back_ptr), _vp(out_ptr), n_pixels,
+                                         termination_alpha, _vp(stream)))
+
+
+def finalize_rgba8(device: int, accum_ptr: int, out_ptr: int, n_pixels: int, flags: int = 0, stream: int = 0) -> None:
+    check(lib().pyvr_cuda_finalize_rgba8(device, _vp(accum_ptr), _vp(out_ptr), n_pixels, flags, _vp(stream)))
+
+
+def stream_synchronize(device: int, stream: int = 0) -> None:
+    check(lib().pyvr_cuda_stream_synchronize(device, _vp(stream)))
 
 
 class PinnedBuffer:

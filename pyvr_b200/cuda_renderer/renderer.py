@@ -224,6 +224,46 @@ class CudaVolumeRenderer:
         _cabi.check(self._lib.pyvr_cuda_render_batch(self._ctx, views, n, out.ctypes.data, 0))
         return out
 
+    def load_brick(self, data: np.ndarray, normals: Optional[np.ndarray], global_shape, origin, own_lo, own_hi,
+                   min_bounds, max_bounds) -> None:
+        """Sort-last: load the sub-block ``data = whole[origin : origin + data.shape]`` (``data[ix,iy,iz]``,
+        i.e. numpy axis k = world axis k) of a volume of ``global_shape`` voxels with bounds
+        ``min_bounds..max_bounds``; this renderer then produces only the samples whose voxel coordinate
+        lies in ``[own_lo, own_hi)`` (see ``pyvr_cuda_upload_brick``; ``pyvr_b200.multi_gpu.split_bricks``
+        computes the triples, ghost layer included)."""
+        data = np.ascontiguousarray(data, dtype=np.float32)
+        if data.ndim != 3:
+            raise ValueError("Volume data must be 3D")
+        if normals is not None:
+            normals = np.ascontiguousarray(normals, dtype=np.float32)
+            if normals.shape != data.shape + (3,):
+                raise ValueError("Normal volume must have 3 channels (last dimension).")
+        i3 = lambda v: (ctypes.c_int * 3)(*[int(x) for x in v])
+        bmin, bmax = _cabi.vec3(min_bounds), _cabi.vec3(max_bounds)
+        _cabi.check(self._lib.pyvr_cuda_upload_brick(
+            self._ctx, data.ctypes.data, normals.ctypes.data if normals is not None else None,
+            i3(data.shape), i3(global_shape), i3(origin), i3(own_lo), i3(own_hi),
+            _cabi.f32_ptr(bmin), _cabi.f32_ptr(bmax), self._texel_format, 0))
+
+    def set_pixel_shard(self, rank: int, count: int) -> None:
+        """Image-space sharding: march only the 64x64 tile groups of ``rank`` (of ``count``); the frames
+        of all ranks add up to the full frame."""
+        _cabi.check(self._lib.pyvr_cuda_set_pixel_shard(self._ctx, int(rank), int(count)))
+
+    def render_to_device(self, device_ptr: int) -> None:
+        """``render()`` into a device buffer of ``width*height*4`` bytes."""
+        _cabi.check(self._lib.pyvr_cuda_render(self._ctx, ctypes.c_void_p(device_ptr), 1))
+
+    def render_accum_to_device(self, device_ptr: int) -> None:
+        """Pre-blend fragment colours (``width*height`` float4) into a device buffer: a partial image."""
+        _cabi.check(self._lib.pyvr_cuda_render_accum(self._ctx, ctypes.c_void_p(device_ptr), 1))
+
+    def render_accum_relay(self, in_ptr: Optional[int], out_ptr: int) -> None:
+        """Sort-last relay: continue the device image ``in_ptr`` (fragment colours of the bricks in front;
+        ``None`` for the first brick) through this renderer's brick into ``out_ptr`` (may be the same)."""
+        _cabi.check(self._lib.pyvr_cuda_render_accum_relay(
+            self._ctx, ctypes.c_void_p(in_ptr) if in_ptr else None, ctypes.c_void_p(out_ptr)))
+
     def render_accum(self) -> np.ndarray:
         """Fragment colour before blending: ``(height, width, 4) float32`` = (acc_rgb, acc_a)."""
         out = np.empty((self.height, self.width, 4), dtype=np.float32)

@@ -1,0 +1,433 @@
+"""Multi-GPU partitioning of the ray-march path on one NVLink/NVSwitch node (SURVEY.md section 8 e).
+
+The reference is single-device; everything here is new design.  One process per GPU
+(``torch.distributed``, backend ``nccl``; ``gloo`` in the CPU tests), three ways to split the work:
+
+* **views** (config C3): the volume is replicated, view ``k`` goes to rank ``k mod P``; no data-path
+  collective (:func:`shard_views`).
+* **image tiles** (config C4): the volume is replicated, 64x64-pixel tile groups are dealt round-robin
+  (``VolumeRenderer.set_pixel_shard``); every rank produces a full-size frame that is zero outside its
+  tiles, and one ``reduce(SUM)`` over uint8 assembles the frame bit for bit (:func:`reduce_tile_frames`).
+* **sort-last bricks** (config C5): the volume is split into ``P = 2^k`` axis-aligned bricks
+  (:func:`brick_grid`, :func:`split_bricks`); every rank marches its brick on the global sample lattice into
+  a partial image (premultiplied float RGBA) and the images are merged by **binary swap**
+  (:func:`binary_swap_plan`): in round ``r`` rank ``i`` exchanges half of its current pixel range with rank
+  ``i XOR 2^r`` and composites ``front over back``; front/back follows from the camera position and the
+  plane that separates the two groups of bricks.  After ``k`` rounds every rank owns ``1/P`` of the pixels,
+  finalises them to RGBA8 and the pieces are gathered.
+
+The plan functions are pure Python (tested on CPU, also with ``gloo`` world_size 2/4); the executors run
+the CUDA kernels of ``csrc/composite.cu`` through the C ABI.  Two exchange paths exist on the GPU:
+``"nccl"`` (send/recv of the half images, then a local merge) and ``"p2p"`` (CUDA IPC: the merge kernel
+reads the partner's half straight out of its memory across NVLink, so transfer and merge are one kernel).
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+__all__ = [
+    "shard_views", "brick_grid", "rank_to_brick", "Brick", "split_bricks", "SwapRound", "binary_swap_plan",
+    "final_piece", "front_is_low_side", "relay_order", "composite_in_process", "SortLastSession", "RelaySession",
+    "reduce_tile_frames",
+]
+
+
+# --------------------------------------------------------------------------------------------------
+# views
+# --------------------------------------------------------------------------------------------------
+def shard_views(n_views: int, rank: int, world: int) -> List[int]:
+    """Indices of the views rank ``rank`` renders: ``k`` with ``k mod world == rank``."""
+    if not 0 <= rank < world:
+        raise ValueError(f"rank {rank} outside world of {world}")
+    return list(range(rank, n_views, world))
+
+
+# --------------------------------------------------------------------------------------------------
+# bricks
+# --------------------------------------------------------------------------------------------------
+def _log2_exact(world: int) -> int:
+    k = world.bit_length() - 1
+    if world < 1 or (1 << k) != world:
+        raise ValueError(f"sort-last needs a power-of-two number of ranks, got {world}")
+    return k
+
+
+def brick_grid(world: int) -> Tuple[int, int, int]:
+    """Bricks per axis for ``world = 2^k`` ranks: bit ``r`` of the rank splits axis ``r mod 3``."""
+    k = _log2_exact(world)
+    grid = [1, 1, 1]
+    for r in range(k):
+        grid[r % 3] *= 2
+    return tuple(grid)
+
+
+def rank_to_brick(rank: int, world: int) -> Tuple[int, int, int]:
+    """Brick coordinates of a rank: bits ``r, r+3, r+6, ...`` of the rank are the bits of axis ``r``'s index."""
+    k = _log2_exact(world)
+    b = [0, 0, 0]
+    for r in range(k):
+        b[r % 3] |= ((rank >> r) & 1) << (r // 3)
+    return tuple(b)
+
+
+@dataclass(frozen=True)
+class Brick:
+    """One brick of a ``shape`` volume, world order (x, y, z) = numpy axes (0, 1, 2)."""
+    coord: Tuple[int, int, int]
+    origin: Tuple[int, int, int]      # first stored voxel
+    dims: Tuple[int, int, int]        # stored voxels (ghost layer included)
+    own_lo: Tuple[int, int, int]      # owns samples with voxel coordinate in [own_lo, own_hi) ...
+    own_hi: Tuple[int, int, int]      # ... open-ended on the volume's outer faces
+
+    def slices(self):
+        return tuple(slice(o, o + d) for o, d in zip(self.origin, self.dims))
+
+
+def _split_points(n: int, parts: int) -> List[int]:
+    # multiples of 16 keep the packed lines (8 or 16 texels) and 8^3 macrocells aligned with the volume's
+    pts = [0]
+    for i in range(1, parts):
+        p = (n * i) // parts
+        if n >= 32 * parts:
+            p = (p // 16) * 16
+        pts.append(max(p, pts[-1] + 1))
+    pts.append(n)
+    if any(b <= a for a, b in zip(pts, pts[1:])):
+        raise ValueError(f"axis of {n} voxels cannot be cut into {parts} bricks")
+    return pts
+
+
+def split_bricks(shape: Sequence[int], grid: Sequence[int]) -> List[Brick]:
+    """Cut a volume of ``shape`` voxels into ``grid`` bricks.  Brick ``b`` owns ``[p[b], p[b+1])`` per axis and
+    stores one extra voxel on the upper side (the +1 ghost layer its upper trilinear taps reach)."""
+    pts = [_split_points(int(n), int(g)) for n, g in zip(shape, grid)]
+    bricks = []
+    for bz in range(grid[2]):
+        for by in range(grid[1]):
+            for bx in range(grid[0]):
+                c = (bx, by, bz)
+                lo = tuple(pts[a][c[a]] for a in range(3))
+                hi = tuple(pts[a][c[a] + 1] for a in range(3))
+                stored_hi = tuple(min(hi[a] + 1, int(shape[a])) for a in range(3))
+                bricks.append(Brick(c, lo, tuple(stored_hi[a] - lo[a] for a in range(3)), lo, hi))
+    return bricks
+
+
+def brick_of_rank(shape: Sequence[int], rank: int, world: int) -> Brick:
+    grid = brick_grid(world)
+    coord = rank_to_brick(rank, world)
+    for b in split_bricks(shape, grid):
+        if b.coord == coord:
+            return b
+    raise AssertionError("unreachable")
+
+
+# --------------------------------------------------------------------------------------------------
+# binary swap
+# --------------------------------------------------------------------------------------------------
+@dataclass(frozen=True)
+class SwapRound:
+    round: int
+    partner: int
+    axis: int                 # world axis of the plane separating the two groups
+    plane_brick: int          # the plane sits at the lower face of this brick index along `axis`
+    low_side: bool            # this rank's group is on the low-coordinate side of the plane
+    keep: Tuple[int, int]     # pixel range [lo, hi) this rank keeps (and receives from the partner)
+    give: Tuple[int, int]     # pixel range it hands to the partner
+
+
+def binary_swap_plan(rank: int, world: int, n_pixels: int) -> List[SwapRound]:
+    """The exchange schedule of one rank.  Ranges are over the flattened pixel index (row-major, row 0 =
+    bottom, as frames are stored)."""
+    k = _log2_exact(world)
+    coord = rank_to_brick(rank, world)
+    lo, hi = 0, n_pixels
+    plan = []
+    for r in range(k):
+        axis, level = r % 3, r // 3
+        bit = (rank >> r) & 1
+        mid = (lo + hi) // 2
+        keep, give = ((lo, mid), (mid, hi)) if bit == 0 else ((mid, hi), (lo, mid))
+        group = coord[axis] >> (level + 1)
+        plane_brick = (group << (level + 1)) + (1 << level)
+        plan.append(SwapRound(r, rank ^ (1 << r), axis, plane_brick, bit == 0, keep, give))
+        lo, hi = keep
+    return plan
+
+
+def final_piece(rank: int, world: int, n_pixels: int) -> Tuple[int, int]:
+    """Pixel range a rank owns after all rounds."""
+    plan = binary_swap_plan(rank, world, n_pixels)
+    return plan[-1].keep if plan else (0, n_pixels)
+
+
+def front_is_low_side(camera_voxel: Sequence[float], axis: int, plane_voxel: float) -> bool:
+    """The group on the low side of the plane ``x[axis] = plane_voxel`` is in front iff the camera is on that
+    side (the plane separates two convex sets, so the order is the same for every ray).  A camera exactly
+    on the plane sees at most one of the groups through any pixel; either answer is right."""
+    return float(camera_voxel[axis]) < float(plane_voxel)
+
+
+def relay_order(world: int, shape: Sequence[int], camera_voxel: Sequence[float]) -> List[int]:
+    """Ranks front to back: the total order the plane rule induces (the same one binary swap composites in).
+    Passing one accumulating image through the bricks in this order (``render_accum_relay``) reproduces
+    the single-GPU march exactly."""
+    k = _log2_exact(world)
+    grid = brick_grid(world)
+
+    def rec(ranks: List[int], r: int) -> List[int]:
+        if r < 0:
+            return ranks
+        low = [x for x in ranks if not (x >> r) & 1]
+        high = [x for x in ranks if (x >> r) & 1]
+        step = binary_swap_plan(low[0], world, 1 << k)[r]
+        plane = plane_position(shape, grid, step.axis, step.plane_brick)
+        first, second = (low, high) if front_is_low_side(camera_voxel, step.axis, plane) else (high, low)
+        return rec(first, r - 1) + rec(second, r - 1)
+
+    return rec(list(range(world)), k - 1)
+
+
+def plane_position(shape: Sequence[int], grid: Sequence[int], axis: int, plane_brick: int) -> int:
+    return _split_points(int(shape[axis]), int(grid[axis]))[plane_brick]
+
+
+def camera_in_voxels(camera_pos, min_bounds, max_bounds, shape) -> np.ndarray:
+    """World position -> continuous voxel coordinate (the march's ``x = tc*n - 0.5``)."""
+    p = np.asarray(camera_pos, dtype=np.float64)
+    lo, hi = np.asarray(min_bounds, np.float64), np.asarray(max_bounds, np.float64)
+    return (p - lo) / (hi - lo) * np.asarray(shape, np.float64) - 0.5
+
+
+# --------------------------------------------------------------------------------------------------
+# executors
+# --------------------------------------------------------------------------------------------------
+def composite_in_process(partials: List, shape, camera_voxel, over: Callable, n_pixels: int) -> List[Tuple[Tuple[int, int], object]]:
+    """Run the binary-swap schedule of all ``P = len(partials)`` ranks inside one process.
+
+    ``partials[rank]`` is any indexable image (``[lo:hi]`` slicing over pixels); ``over(front, back)`` returns
+    the merged slice.  Returns ``[(pixel range, merged slice)]`` per rank.  Used by the CPU tests (numpy
+    ``over``) and by the single-GPU emulation of the brick path (device buffers, CUDA ``over``)."""
+    world = len(partials)
+    k = _log2_exact(world)
+    grid = brick_grid(world)
+    plans = [binary_swap_plan(r, world, n_pixels) for r in range(world)]
+    current = list(partials)
+    for r in range(k):
+        nxt = [None] * world
+        for rank in range(world):
+            step = plans[rank][r]
+            mine, theirs = current[rank], current[step.partner]
+            plane = plane_position(shape, grid, step.axis, step.plane_brick)
+            i_am_front = front_is_low_side(camera_voxel, step.axis, plane) == step.low_side
+            lo, hi = step.keep
+            a, b = _slice(mine, lo, hi, r, plans[rank]), _slice(theirs, lo, hi, r, plans[step.partner])
+            nxt[rank] = over(a, b) if i_am_front else over(b, a)
+        current = nxt
+    return [((plans[r][-1].keep if k else (0, n_pixels)), current[r]) for r in range(world)]
+
+
+def _slice(image, lo, hi, r, plan):
+    """Slice ``[lo, hi)`` of a rank's image at round ``r``: round 0 images are full frames, later ones start at
+    the range kept in round ``r - 1``."""
+    base = 0 if r == 0 else plan[r - 1].keep[0]
+    return image[lo - base:hi - base]
+
+
+class RelaySession:
+    """Exact sort-last: one accumulating image travels through the ranks in visibility order
+    (:func:`relay_order`); every rank continues the march through its own brick
+    (``VolumeRenderer.render_accum_relay``).  No compositing kernel, no approximation of the stop rule; a
+    frame costs P brick marches in sequence, but consecutive views pipeline across the ranks."""
+
+    def __init__(self, shape, min_bounds, max_bounds, n_pixels: int, *, group=None, device: int = 0):
+        import torch
+        import torch.distributed as dist
+
+        self.torch, self.dist, self.group = torch, dist, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.shape = tuple(int(s) for s in shape)
+        self.min_bounds, self.max_bounds = np.asarray(min_bounds, np.float64), np.asarray(max_bounds, np.float64)
+        self.n_pixels, self.device = int(n_pixels), device
+        self.brick = brick_of_rank(self.shape, self.rank, self.world)
+        self.image = torch.zeros((self.n_pixels, 4), dtype=torch.float32, device=f"cuda:{device}")
+
+    def render(self, renderer, camera_pos, flags: int = 0):
+        """March this rank's brick for the current camera of ``renderer``.  Returns the RGBA8 frame (uint8
+        ``(n_pixels, 4)`` tensor) on the LAST rank of the order, ``None`` elsewhere."""
+        from .cuda_renderer import _cabi
+
+        cam = camera_in_voxels(camera_pos, self.min_bounds, self.max_bounds, self.shape)
+        order = relay_order(self.world, self.shape, cam)
+        pos = order.index(self.rank)
+        if pos > 0:
+            self.dist.recv(self.image, src=order[pos - 1], group=self.group)
+        self.torch.cuda.current_stream().synchronize()
+        renderer.render_accum_relay(self.image.data_ptr() if pos > 0 else None, self.image.data_ptr())
+        if pos + 1 < self.world:
+            self.dist.send(self.image, dst=order[pos + 1], group=self.group)
+            return None
+        out = self.torch.empty((self.n_pixels, 4), dtype=self.torch.uint8, device=self.image.device)
+        _cabi.finalize_rgba8(self.device, self.image.data_ptr(), out.data_ptr(), self.n_pixels, flags,
+                             self.torch.cuda.current_stream().cuda_stream)
+        return out
+
+
+class SortLastSession:
+    """Binary-swap compositing across the ranks of a ``torch.distributed`` process group.
+
+    ``exchange``: ``"nccl"`` -- send/recv the half images through the process group, merge locally;
+    ``"p2p"`` -- every rank's image lives in an IPC-shared ``cudaMalloc`` buffer and the merge kernel reads the
+    partner's half directly over NVLink (rounds are fenced with a barrier).  With the ``gloo`` backend (CPU
+    tests) images are CPU tensors and ``over`` must be supplied.
+    """
+
+    def __init__(self, shape, min_bounds, max_bounds, n_pixels: int, *, group=None, device: Optional[int] = None,
+                 exchange: str = "nccl", over: Optional[Callable] = None, termination_alpha: float = 0.99):
+        import torch
+        import torch.distributed as dist
+
+        self.torch, self.dist = torch, dist
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.shape = tuple(int(s) for s in shape)
+        self.min_bounds, self.max_bounds = np.asarray(min_bounds, np.float64), np.asarray(max_bounds, np.float64)
+        self.n_pixels = int(n_pixels)
+        self.grid = brick_grid(self.world)
+        self.brick = brick_of_rank(self.shape, self.rank, self.world)
+        self.plan = binary_swap_plan(self.rank, self.world, self.n_pixels)
+        self.device = device
+        self.exchange = exchange
+        self.term = float(termination_alpha)
+        self._over = over
+        self._peers = {}
+        self.image = None          # float32 (n_pixels, 4)
+        self._own = None
+        if exchange == "p2p":
+            self._setup_p2p()
+        elif exchange != "nccl":
+            raise ValueError("exchange must be 'nccl' or 'p2p'")
+
+    # -- buffers ---------------------------------------------------------------------------------
+    def _setup_p2p(self):
+        from .cuda_renderer import _cabi
+
+        self._own = _cabi.DeviceBuffer(self.n_pixels * 16, self.device)
+        handles = [None] * self.world
+        self.dist.all_gather_object(handles, self._own.ipc_handle(), group=self.group)
+        for step in self.plan:
+            self._peers[step.partner] = _cabi.PeerBuffer(handles[step.partner], self.device)
+
+    def image_ptr(self) -> int:
+        """Device pointer the renderer writes its partial image to (``render_accum_to_device``)."""
+        if self.exchange == "p2p":
+            return self._own.ptr
+        if self.image is None:
+            self.image = self.torch.zeros((self.n_pixels, 4), dtype=self.torch.float32, device=f"cuda:{self.device}")
+        return self.image.data_ptr()
+
+    # -- compositing -----------------------------------------------------------------------------
+    def _i_am_front(self, step: SwapRound, camera_voxel) -> bool:
+        plane = plane_position(self.shape, self.grid, step.axis, step.plane_brick)
+        return front_is_low_side(camera_voxel, step.axis, plane) == step.low_side
+
+    def composite(self, camera_pos, image=None):
+        """Merge the partial images of all ranks.  Returns ``((lo, hi), piece)``: this rank's fully composited
+        pixel range (a float32 ``(hi-lo, 4)`` tensor, or for ``"p2p"`` the device pointer of that range)."""
+        cam = camera_in_voxels(camera_pos, self.min_bounds, self.max_bounds, self.shape)
+        if self.exchange == "p2p":
+            return self._composite_p2p(cam)
+        torch, dist = self.torch, self.dist
+        img = self.image if image is None else image
+        base = 0
+        for step in self.plan:
+            klo, khi = step.keep
+            glo, ghi = step.give
+            give = img[glo - base:ghi - base].contiguous()
+            keep = img[klo - base:khi - base]
+            recv = torch.empty_like(keep)
+            ops = [dist.P2POp(dist.isend, give, step.partner, group=self.group),
+                   dist.P2POp(dist.irecv, recv, step.partner, group=self.group)]
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+            front, back = (keep, recv) if self._i_am_front(step, cam) else (recv, keep)
+            img = self._merge(front, back)
+            base = klo
+        lo, hi = self.plan[-1].keep if self.plan else (0, self.n_pixels)
+        return (lo, hi), img
+
+    def _merge(self, front, back):
+        if self._over is not None:
+            return self._over(front, back)
+        from .cuda_renderer import _cabi
+
+        out = self.torch.empty_like(front)
+        stream = self.torch.cuda.current_stream().cuda_stream
+        _cabi.composite_over(self.device, front.data_ptr(), back.data_ptr(), out.data_ptr(), front.shape[0],
+                             self.term, stream)
+        return out
+
+    def _composite_p2p(self, cam):
+        from .cuda_renderer import _cabi
+
+        torch, dist = self.torch, self.dist
+        stream = torch.cuda.current_stream().cuda_stream
+        for step in self.plan:
+            # the partner's current image must be complete before it is read, and nobody may still be reading
+            # the range this rank is about to overwrite
+            torch.cuda.synchronize()
+            dist.barrier(group=self.group)
+            klo, khi = step.keep
+            mine = self._own.ptr + klo * 16
+            theirs = self._peers[step.partner].ptr + klo * 16
+            front, back = (mine, theirs) if self._i_am_front(step, cam) else (theirs, mine)
+            # fused transfer + merge: the kernel loads the partner's half across NVLink and writes in place
+            _cabi.composite_over(self.device, front, back, mine, khi - klo, self.term, stream)
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        lo, hi = self.plan[-1].keep if self.plan else (0, self.n_pixels)
+        return (lo, hi), self._own.ptr + lo * 16
+
+    # -- final frame -----------------------------------------------------------------------------
+    def gather_rgba8(self, piece_range, piece, flags: int = 0, dst: int = 0):
+        """Finalise this rank's piece to RGBA8 and gather the frame on rank ``dst`` (``None`` elsewhere)."""
+        from .cuda_renderer import _cabi
+
+        torch, dist = self.torch, self.dist
+        lo, hi = piece_range
+        n = hi - lo
+        per = -(-self.n_pixels // self.world)            # pieces differ by at most one pixel: pad to the largest
+        out = torch.zeros((per, 4), dtype=torch.uint8, device=f"cuda:{self.device}")
+        ptr = piece if isinstance(piece, int) else piece.contiguous().data_ptr()
+        _cabi.finalize_rgba8(self.device, ptr, out.data_ptr(), n, flags, torch.cuda.current_stream().cuda_stream)
+        gathered = [torch.empty_like(out) for _ in range(self.world)] if self.rank == dst else None
+        dist.gather(out, gathered, dst=dst, group=self.group)
+        if self.rank != dst:
+            return None
+        frame = torch.empty((self.n_pixels, 4), dtype=torch.uint8, device=out.device)
+        for r in range(self.world):
+            rlo, rhi = final_piece(r, self.world, self.n_pixels)
+            frame[rlo:rhi] = gathered[r][:rhi - rlo]
+        return frame
+
+    def close(self):
+        for p in self._peers.values():
+            p.close()
+        self._peers = {}
+        if self._own is not None:
+            self._own.close()
+            self._own = None
+
+
+def reduce_tile_frames(frame, dst: int = 0, group=None):
+    """Assemble a tile-sharded frame: per-rank frames are zero outside their own tiles, so a SUM over
+    uint8 is their union.  ``frame``: a uint8 tensor (CUDA with nccl, CPU with gloo); reduced in place on
+    ``dst``."""
+    import torch.distributed as dist
+
+    dist.reduce(frame, dst=dst, op=dist.ReduceOp.SUM, group=group)
+    return frame
