@@ -124,6 +124,22 @@ int pyvr_cuda_upload_brick(pyvr_ctx *ctx, const float *scalar, const float *norm
                            const int own_lo[3], const int own_hi[3],
                            const float bmin[3], const float bmax[3], int texel_format, int src_is_device);
 
+/* Device-side synthetic volume: what
+ *   v = create_sample_volume(size, shape); Volume(v, compute_normal_volume(v), bmin, bmax) -> load_volume
+ * would upload (pyvr/datasets/synthetic.py:10-122), generated and packed on the device without touching
+ * the host.  With origin/local_dims/own_lo/own_hi non-NULL only that sub-block is generated, as a
+ * sort-last brick (arguments as pyvr_cuda_upload_brick); all NULL = the whole volume.  kernel_ms (may be
+ * NULL) receives the device time of generation + pack. */
+#define PYVR_SHAPE_SPHERE 0
+#define PYVR_SHAPE_TORUS 1
+#define PYVR_SHAPE_DOUBLE_SPHERE 2
+int pyvr_cuda_generate_volume(pyvr_ctx *ctx, int shape, int size, const int local_dims[3], const int origin[3],
+                              const int own_lo[3], const int own_hi[3], const float bmin[3], const float bmax[3],
+                              int texel_format, float *kernel_ms);
+/* Test aid: unpack the stored texels into the reference's two arrays (host pointers, numpy C order of the
+ * stored block; either may be NULL). */
+int pyvr_cuda_read_texels(pyvr_ctx *ctx, float *scalar, float *normals);
+
 /* Image-space sharding (SURVEY.md section 8 e, config C4): this context marches the 64x64-pixel tile
  * groups g with g % count == rank and writes zeros elsewhere, so the frames of all ranks add up
  * (e.g. ncclReduce SUM over uint8) to the full frame, bit for bit.  count = 1 restores normal rendering. */

@@ -18,7 +18,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libpyvr_cuda.so")
-SOURCES = ["abi.cu", "march.cu", "volume_pack.cu", "normals.cu", "composite.cu"]
+SOURCES = ["abi.cu", "march.cu", "volume_pack.cu", "normals.cu", "composite.cu", "synth.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
     "--shared", "-Xcompiler", "-fPIC,-ffp-contract=off", "-cudart", "static",

@@ -477,6 +477,92 @@ int pyvr_cuda_upload_brick(pyvr_ctx *c, const float *scalar, const float *normal
     return upload_packed(c, scalar, normals, src_is_device);
 }
 
+int pyvr_cuda_generate_volume(pyvr_ctx *c, int shape, int size, const int local_dims[3], const int origin[3],
+                              const int own_lo[3], const int own_hi[3], const float bmin[3], const float bmax[3],
+                              int texel_format, float *kernel_ms) {
+    if (!c || !bmin || !bmax) return fail(PYVR_ERR_INVALID, "NULL argument");
+    if (shape < PYVR_SHAPE_SPHERE || shape > PYVR_SHAPE_DOUBLE_SPHERE) return fail(PYVR_ERR_INVALID, "unknown shape %d", shape);
+    if (size < 2) return fail(PYVR_ERR_INVALID, "size must be at least 2");
+    if (texel_format != PYVR_TEXEL_F32X4 && texel_format != PYVR_TEXEL_F16X4)
+        return fail(PYVR_ERR_INVALID, "unknown texel format %d", texel_format);
+    const bool brick = local_dims || origin || own_lo || own_hi;
+    if (brick && !(local_dims && origin && own_lo && own_hi))
+        return fail(PYVR_ERR_INVALID, "a brick needs local_dims, origin, own_lo and own_hi");
+    const int global[3] = {size, size, size};
+    for (int a = 0; a < 3; ++a) {
+        if (!(bmax[a] > bmin[a])) return fail(PYVR_ERR_INVALID, "max_bounds must be greater than min_bounds");
+        if (!brick) continue;
+        if (local_dims[a] <= 0 || origin[a] < 0 || origin[a] + local_dims[a] > size)
+            return fail(PYVR_ERR_INVALID, "brick [%d, %d) does not fit axis %d of extent %d", origin[a],
+                        origin[a] + local_dims[a], a, size);
+        const int need_hi = own_hi[a] < size ? own_hi[a] : size - 1;
+        if (own_lo[a] < origin[a] || own_hi[a] <= own_lo[a] || own_hi[a] > size || need_hi > origin[a] + local_dims[a] - 1)
+            return fail(PYVR_ERR_INVALID, "ownership [%d, %d) on axis %d does not fit the brick (+1 ghost layer)", own_lo[a], own_hi[a], a);
+    }
+    DeviceGuard guard(c->device);
+    CU(cudaStreamSynchronize(c->stream));
+    free_volume(c);
+    c->half_texels = texel_format == PYVR_TEXEL_F16X4;
+    if (brick) fill_volume_desc(c, local_dims, global, origin, own_lo, own_hi, bmin, bmax);
+    else fill_volume_desc(c, global, nullptr, nullptr, nullptr, nullptr, bmin, bmax);
+
+    const VolumeDesc &v = c->vol;
+    const size_t n_tex = texel_count(c);
+    c->texel_bytes = n_tex * (c->half_texels ? 8 : 16);
+    c->n_cells = (size_t)v.ncell[0] * v.ncell[1] * v.ncell[2];
+    CU(cudaMalloc(&c->texels, c->texel_bytes));
+    CU(cudaMalloc(&c->cell_minmax, c->n_cells * sizeof(float2)));
+    CU(cudaMalloc(&c->cell_dist, c->n_cells));
+    CU(cudaMalloc(&c->cell_scratch, c->n_cells));
+    CU(cudaMalloc(&c->active_box, 6 * sizeof(int)));
+    if (n_tex != (size_t)v.n[0] * v.n[1] * v.n[2]) CU(cudaMemsetAsync(c->texels, 0, c->texel_bytes, c->stream));
+    c->vol.texels = c->texels;
+    c->vol.cell_dist = c->cell_dist;
+    c->vol.active_box = c->active_box;
+
+    // slab scratch: about 1 GiB, at least 3 planes
+    const size_t plane = (size_t)(v.n[1] + 2) * (size_t)(v.n[2] + 2);
+    size_t planes = ((size_t)1 << 28) / plane;
+    if (planes < 3) planes = 3;
+    if (planes > (size_t)v.n[0] + 2) planes = (size_t)v.n[0] + 2;
+    float *scratch = nullptr;
+    CU(cudaMalloc(&scratch, planes * plane * sizeof(float)));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaError_t e = cudaEventCreate(&e0);
+    if (e == cudaSuccess) e = cudaEventCreate(&e1);
+    if (e == cudaSuccess) e = cudaEventRecord(e0, c->stream);
+    if (e == cudaSuccess) e = launch_synth_volume(c->vol, c->half_texels, shape, size, scratch, planes * plane, c->stream);
+    if (e == cudaSuccess) e = cudaEventRecord(e1, c->stream);
+    if (e == cudaSuccess) e = launch_cell_minmax(c->vol, c->half_texels, c->cell_minmax, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e == cudaSuccess && kernel_ms) e = cudaEventElapsedTime(kernel_ms, e0, e1);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    cudaFree(scratch);
+    CU(e);
+    c->have_volume = true;
+    return classify_cells(c);
+}
+
+int pyvr_cuda_read_texels(pyvr_ctx *c, float *scalar, float *normals) {
+    if (!c) return fail(PYVR_ERR_INVALID, "ctx is NULL");
+    if (!c->have_volume) return fail(PYVR_ERR_STATE, "no volume loaded");
+    DeviceGuard guard(c->device);
+    const size_t voxels = (size_t)c->vol.n[0] * c->vol.n[1] * c->vol.n[2];
+    float *d_s = nullptr, *d_n = nullptr;
+    cudaError_t e = cudaSuccess;
+    if (scalar) e = cudaMalloc(&d_s, voxels * sizeof(float));
+    if (e == cudaSuccess && normals) e = cudaMalloc(&d_n, voxels * 3 * sizeof(float));
+    if (e == cudaSuccess) e = launch_unpack_texels(c->vol, c->half_texels, d_s, d_n, c->stream);
+    if (e == cudaSuccess && scalar) e = cudaMemcpyAsync(scalar, d_s, voxels * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess && normals) e = cudaMemcpyAsync(normals, d_n, voxels * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_s);
+    cudaFree(d_n);
+    CU(e);
+    return PYVR_OK;
+}
+
 int pyvr_cuda_set_pixel_shard(pyvr_ctx *c, int rank, int count) {
     if (!c) return fail(PYVR_ERR_INVALID, "ctx is NULL");
     if (count < 1 || rank < 0 || rank >= count) return fail(PYVR_ERR_INVALID, "shard %d of %d", rank, count);

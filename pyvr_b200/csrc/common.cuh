@@ -115,6 +115,11 @@ constexpr int kCellDistSweeps = 14;   // relaxation sweeps: every distance <= 14
 cudaError_t launch_cell_classify(const float2 *cell_minmax, const VolumeDesc &vol, const float4 *lut,
                                  int lut_size, uint8_t *cell_dist, uint8_t *cell_scratch, int *active_box,
                                  cudaStream_t stream);
+// synth.cu: analytic volume -> packed texels (scalar + normals), slab by slab through `scratch`
+cudaError_t launch_synth_volume(const VolumeDesc &vol, bool half_texels, int shape, int size, float *scratch,
+                                size_t scratch_floats, cudaStream_t stream);
+cudaError_t launch_unpack_texels(const VolumeDesc &vol, bool half_texels, float *scalar, float *normals,
+                                 cudaStream_t stream);
 cudaError_t launch_normals(const float *in, float *out, int n0, int n1, int n2, cudaStream_t stream);
 
 }  // namespace pyvr

@@ -20,6 +20,7 @@ ABI_VERSION = 2
 IPC_HANDLE_BYTES = 64
 TEXEL_F32X4, TEXEL_F16X4 = 0, 1
 FLAG_STRICT, FLAG_ESS, FLAG_NO_BLEND = 0x1, 0x2, 0x4
+SHAPES = {"sphere": 0, "torus": 1, "double_sphere": 2}
 
 # name -> (restype, argtypes); every symbol include/pyvr_cuda.h declares
 _c = ctypes
@@ -60,6 +61,8 @@ SYMBOLS = {
     "pyvr_cuda_set_stream": (_i, [_vp, _vp]),
     "pyvr_cuda_upload_volume": (_i, [_vp, _vp, _vp, _i, _i, _i, _fp, _fp, _i, _i]),
     "pyvr_cuda_upload_brick": (_i, [_vp, _vp, _vp, _ip, _ip, _ip, _ip, _ip, _fp, _fp, _i, _i]),
+    "pyvr_cuda_generate_volume": (_i, [_vp, _i, _i, _ip, _ip, _ip, _ip, _fp, _fp, _i, _fp]),
+    "pyvr_cuda_read_texels": (_i, [_vp, _vp, _vp]),
     "pyvr_cuda_set_pixel_shard": (_i, [_vp, _i, _i]),
     "pyvr_cuda_set_lut": (_i, [_vp, _vp, _i]),
     "pyvr_cuda_set_camera": (_i, [_vp, _fp, _fp, _fp]),

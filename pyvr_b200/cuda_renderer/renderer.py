@@ -245,6 +245,31 @@ class CudaVolumeRenderer:
             i3(data.shape), i3(global_shape), i3(origin), i3(own_lo), i3(own_hi),
             _cabi.f32_ptr(bmin), _cabi.f32_ptr(bmax), self._texel_format, 0))
 
+    def generate_volume(self, size: int, shape: str = "double_sphere", min_bounds=(-0.5, -0.5, -0.5),
+                        max_bounds=(0.5, 0.5, 0.5), brick=None) -> float:
+        """Device-side equivalent of ``create_sample_volume(size, shape)`` + ``compute_normal_volume`` +
+        ``load_volume`` (nothing crosses PCIe).  ``brick``: a ``pyvr_b200.multi_gpu.Brick`` to generate only
+        that sub-block for sort-last rendering.  Returns the device time in milliseconds.  ``self.volume``
+        stays ``None``: the data exists only in packed form on the device."""
+        if shape not in _cabi.SHAPES:
+            raise ValueError(f"Unknown shape: {shape}. Device-side shapes: {', '.join(_cabi.SHAPES)}")
+        i3 = lambda v: (ctypes.c_int * 3)(*[int(x) for x in v])
+        bmin, bmax = _cabi.vec3(min_bounds), _cabi.vec3(max_bounds)
+        ms = ctypes.c_float(0.0)
+        args = (i3(brick.dims), i3(brick.origin), i3(brick.own_lo), i3(brick.own_hi)) if brick is not None else (None,) * 4
+        _cabi.check(self._lib.pyvr_cuda_generate_volume(
+            self._ctx, _cabi.SHAPES[shape], int(size), *args, _cabi.f32_ptr(bmin), _cabi.f32_ptr(bmax),
+            self._texel_format, ctypes.byref(ms)))
+        self.volume = None
+        return ms.value
+
+    def read_texels(self, shape) -> tuple:
+        """Test aid: the stored block unpacked to ``(scalar (shape), normals (shape + (3,)))`` float32."""
+        scalar = np.empty(tuple(shape), dtype=np.float32)
+        normals = np.empty(tuple(shape) + (3,), dtype=np.float32)
+        _cabi.check(self._lib.pyvr_cuda_read_texels(self._ctx, scalar.ctypes.data, normals.ctypes.data))
+        return scalar, normals
+
     def set_pixel_shard(self, rank: int, count: int) -> None:
         """Image-space sharding: march only the 64x64 tile groups of ``rank`` (of ``count``); the frames
         of all ranks add up to the full frame."""
