@@ -47,9 +47,13 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--size", type=int, default=512)
-    ap.add_argument("--width", type=int, default=1920)
-    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--workload", default="c3", choices=["c3", "c4", "c5"],
+                    help="c3 = headline turntable (default); c4 = image tiles over a replicated device-generated "
+                         "volume; c5 = sort-last bricks + binary swap (secondary lines, see DESIGN.md)")
+    ap.add_argument("--size", type=int, default=None, help="volume edge (default 512 / 2048 / 2048*cbrt(N))")
+    ap.add_argument("--width", type=int, default=None)
+    ap.add_argument("--height", type=int, default=None)
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="c5: binary-swap exchange path")
     ap.add_argument("--views-per-step", type=int, default=12)
     ap.add_argument("--texels", default="f32", choices=["f32", "f16"])
     ap.add_argument("--no-ess", action="store_true", help="disable empty-space skipping")
@@ -231,11 +235,29 @@ def workload_config(args, stride_note=None):
     return cfg
 
 
+def traffic_per_view(args):
+    """DRAM bytes one view of the march moves, from the committed ncu capture (profiles/r01_traffic.json)."""
+    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        table = json.load(open(path))
+        key = f"{args.texels}_{'dense' if args.no_ess else 'ess'}"
+        return float(table["c3_dram_bytes_per_view"][key])
+    except Exception:
+        return None
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.workload != "c3":
+        import bench_partitioned
+
+        bench_partitioned.run(args, rank, world, local_rank)
+        return
+    args.size = args.size or 512
+    args.width, args.height = args.width or 1920, args.height or 1080
     if args.impl == "reference":
         run_reference(args, rank)
         return
@@ -342,6 +364,10 @@ def main():
         peak, peak_src = measured_peak_gbs()
         launch_ms = kernel_ms / max(launches, 1)
         achieved = (fetched / max(launches, 1)) * bytes_per_sample / (launch_ms * 1e-3) / 1e9
+        views_per_launch = per_step if per_step <= 16 else 16
+        per_view = traffic_per_view(args)
+        sm_mhz = clocks.summary().get("sm_mhz") or 1965.0
+        l1_peak = 148 * 128 * sm_mhz * 1e6 / 1e9      # one 128-byte L1 wavefront per SM per clock
         line = {
             "metric": "ray-march throughput", "value": value, "unit": "Gsamples/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
@@ -350,19 +376,27 @@ def main():
             "frames_per_s": frames / (ms * 1e-3),
             "samples_per_frame": all_samples / frames,
             "e2e": {"value": e2e_value, "unit": "Gsamples/s", "frames_per_s": frames / (e2e_ms * 1e-3),
-                    "h2d_bytes_per_step": per_step * ctypes.sizeof(_cabi.View), "d2h_bytes_per_step": per_step * frame_bytes,
+                    "h2d_bytes_per_step": world * per_step * ctypes.sizeof(_cabi.View),
+                    "d2h_bytes_per_step": world * per_step * frame_bytes,
                     "api": "VolumeRenderer.render_batch(views, out=pinned host buffer)", "frame_checksum": checksum},
             "gpu_launches": int(launches),
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "kernel": "march_kernel<fast>",
-                "kernel_ms_per_launch": launch_ms, "views_per_launch": per_step if per_step <= 16 else 16,
+                "traffic": per_view * views_per_launch if per_view else None,
+                "traffic_source": "profiles/r01_traffic.json (ncu dram__bytes_read+write of a 1-view launch x views per launch)",
+                "peak_source": peak_src, "kernel": "march_kernel<fast>",
+                "kernel_ms_per_launch": launch_ms, "views_per_launch": views_per_launch,
+                "l1": {"bound": "l1tex data stage", "achieved": achieved, "peak": l1_peak, "unit": "GB/s",
+                       "frac": achieved / l1_peak,
+                       "note": "same algorithmic bytes against 148 SMs x 128 B/clk at the sampled SM clock: the unit "
+                               "that actually binds this gather kernel (ncu: l1tex data-stage 69-91 % busy, DRAM 5-11 %)"},
                 "algorithmic_bytes_per_sample": bytes_per_sample,
                 "samples_fetched_per_launch": fetched / max(launches, 1),
                 "samples_reference_per_launch": samples / max(launches, 1),
                 "kernel_share_of_step": kernel_ms / ms if world == 1 else None,
-                "note": "achieved = fetched samples x 8 texels x texel bytes / march-kernel time (gathers are served "
-                        "by L1/L2, so this can exceed the HBM copy peak; DRAM traffic is in profiles/)",
+                "note": "achieved = fetched samples x 8 texels x texel bytes / march-kernel time.  The gather is served "
+                        "by L1/L2 (each packed line is read from HBM about once per view: `traffic`), so the "
+                        "fraction of the HBM copy rate exceeds 1; see `l1` for the binding unit",
             },
             "clocks": clocks.summary(),
             "normals_kernel": {"ms": normals_ms, "GB/s": args.size ** 3 * 16 / (normals_ms * 1e-3) / 1e9,
