@@ -35,6 +35,7 @@ int fail(int code, const char *fmt, ...) {
                         "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
+constexpr size_t kPairBudget = (size_t)40 << 30;   // auto z-pair layout up to 40 GiB of packed texels
 constexpr int kRing = 3;  // device frame slots used to overlap march and device->host copies
 
 struct DeviceGuard {
@@ -68,6 +69,8 @@ struct pyvr_ctx {
     size_t n_cells = 0;
     bool swizzle = true;  // L1 bank swizzle of the texel layout (common.cuh); off only for A/B profiling
     int shard_rank = 0, shard_count = 1;   // image-space tile sharding (pyvr_cuda_set_pixel_shard)
+    int pair_option = -1;   // z-pair entries: -1 auto (when the doubled array stays under kPairBudget), 0 off, 1 on
+    bool use_pair = false;  // decided per upload
 
     // transfer function
     float4 *lut = nullptr;
@@ -154,10 +157,17 @@ void inverse4_f32(const float *m, float *o) {
     o[15] = (a20 * b03 - a21 * b01 + a22 * b00) * id;
 }
 
+// z-pair layout (common.cuh) for this upload?
+void choose_pair(pyvr_ctx *c, const int local[3]) {
+    const size_t doubled = (size_t)local[0] * local[1] * local[2] * (c->half_texels ? 8 : 16) * 2;
+    c->use_pair = c->pair_option < 0 ? doubled <= kPairBudget : c->pair_option != 0;
+}
+
 // local[3] = stored texel counts along world x, y, z; global/org/own_* = NULL for a whole volume.
 void fill_volume_desc(pyvr_ctx *c, const int local[3], const int global[3], const int org[3],
                       const int own_lo[3], const int own_hi[3], const float bmin[3], const float bmax[3]) {
     VolumeDesc &v = c->vol;
+    choose_pair(c, local);
     v.bricked = global != nullptr;
     for (int a = 0; a < 3; ++a) {
         v.n[a] = local[a];
@@ -173,10 +183,20 @@ void fill_volume_desc(pyvr_ctx *c, const int local[3], const int global[3], cons
         v.ncell[a] = (v.n[a] + 7) / 8;
     }
     // lines of SLOTS consecutive-z texels with an optional slot rotation; see common.cuh
-    v.slot_shift = c->half_texels ? 4 : 3;
+    v.pair = c->use_pair ? 1 : 0;
+    v.slot_shift = (c->half_texels ? 4 : 3) - v.pair;
     v.row_lines = (v.n[2] + (1 << v.slot_shift) - 1) >> v.slot_shift;
-    v.swz_x = c->swizzle ? 1 : 0;
-    v.swz_y = c->swizzle ? 3 : 0;
+    // slot = (iz + ix + 3*iy) mod SLOTS.  Measured best on C3 among the linear maps tried, including the ones
+    // with the longest shortest collision vector ((2,4,1) mod 8, (1,3,5) mod 16; tools/swizzle_search.py), which
+    // are 10 % slower on the dense march: what matters is that the texels one quarter-warp touches -- a short
+    // run along the image-row direction -- spread over the banks, not the distance between colliding texels.
+    v.swz_x = 0; v.swz_y = 0; v.swz_z = 1;
+    if (c->swizzle) {
+        v.swz_x = 1; v.swz_y = 3; v.swz_z = 1;
+        const char *env = getenv("PYVR_CUDA_SWZ");   // "x,y,z" override for experiments
+        int ex, ey, ez;
+        if (env && sscanf(env, "%d,%d,%d", &ex, &ey, &ez) == 3 && (ez & 1)) { v.swz_x = ex; v.swz_y = ey; v.swz_z = ez; }
+    }
 }
 
 size_t texel_count(const pyvr_ctx *c) {
@@ -257,7 +277,7 @@ int march(pyvr_ctx *c, int first, int n, uchar4 *out8, float4 *out_acc, size_t e
     a.out_acc = out_acc;
     a.in_acc = in_acc;
     CU(cudaEventRecord(c->ev[2 * ev_pair], c->stream));
-    CU(launch_march(a, n, c->half_texels, c->texel_bytes / (c->half_texels ? 8 : 16) >= ((size_t)1 << 31), c->stream));
+    CU(launch_march(a, n, c->half_texels, c->texel_bytes / entry_bytes(c->half_texels, c->vol.pair) >= ((size_t)1 << 31), c->stream));
     CU(cudaEventRecord(c->ev[2 * ev_pair + 1], c->stream));
     return PYVR_OK;
 }
@@ -313,6 +333,8 @@ int pyvr_cuda_create(int device, int width, int height, pyvr_ctx **out_ctx) {
     c->height = height;
     const char *layout = getenv("PYVR_CUDA_LAYOUT");
     if (layout) c->swizzle = strcmp(layout, "linear") != 0;   // "linear" = no swizzle, anything else = default
+    const char *pair = getenv("PYVR_CUDA_PAIR");
+    if (pair) c->pair_option = atoi(pair);
     // defaults of the reference renderer: balanced preset, Light.default(), bounds +-0.5
     c->params.step_size = 0.01f; c->params.max_steps = 500; c->params.reference_step_size = 0.01f;
     c->params.ambient = 0.2f; c->params.diffuse = 0.8f;
@@ -369,6 +391,10 @@ int pyvr_cuda_set_stream(pyvr_ctx *c, void *cuda_stream) {
 
 int pyvr_cuda_set_option(pyvr_ctx *c, const char *key, int value) {
     if (!c || !key) return fail(PYVR_ERR_INVALID, "ctx or key is NULL");
+    if (strcmp(key, "pair") == 0) {   // takes effect at the next upload
+        c->pair_option = value < 0 ? -1 : (value != 0);
+        return PYVR_OK;
+    }
     if (strcmp(key, "swizzle") == 0) {
         if (c->have_volume && (value != 0) != c->swizzle)
             return fail(PYVR_ERR_STATE, "swizzle must be chosen before the volume is uploaded");
@@ -388,7 +414,7 @@ int upload_packed(pyvr_ctx *c, const float *scalar, const float *normals, int sr
     const VolumeDesc &v = c->vol;
     const size_t voxels = (size_t)v.n[0] * v.n[1] * v.n[2];
     const size_t n_tex = texel_count(c);
-    c->texel_bytes = n_tex * (c->half_texels ? 8 : 16);
+    c->texel_bytes = n_tex * entry_bytes(c->half_texels, c->vol.pair);
     c->n_cells = (size_t)v.ncell[0] * v.ncell[1] * v.ncell[2];
     CU(cudaMalloc(&c->texels, c->texel_bytes));
     CU(cudaMalloc(&c->cell_minmax, c->n_cells * sizeof(float2)));
@@ -508,7 +534,7 @@ int pyvr_cuda_generate_volume(pyvr_ctx *c, int shape, int size, const int local_
 
     const VolumeDesc &v = c->vol;
     const size_t n_tex = texel_count(c);
-    c->texel_bytes = n_tex * (c->half_texels ? 8 : 16);
+    c->texel_bytes = n_tex * entry_bytes(c->half_texels, c->vol.pair);
     c->n_cells = (size_t)v.ncell[0] * v.ncell[1] * v.ncell[2];
     CU(cudaMalloc(&c->texels, c->texel_bytes));
     CU(cudaMalloc(&c->cell_minmax, c->n_cells * sizeof(float2)));

@@ -16,7 +16,7 @@ namespace pyvr {
 // Packed texel array.  Texels {s,nx,ny,nz} live in 128-byte lines of SLOTS = 128/texel_bytes
 // consecutive-z texels (8 for f32x4, 16 for f16x4); lines are ordered x-major, then y, then z:
 //   line(ix,iy,iz) = (ix*n[1] + iy) * row_lines + (iz >> slot_shift)
-//   slot(ix,iy,iz) = (iz + swz_x*ix + swz_y*iy) & (SLOTS-1)
+//   slot(ix,iy,iz) = (swz_z*iz + swz_x*ix + swz_y*iy) & (SLOTS-1)
 //   texel index    = line * SLOTS + slot
 // The slot rotation ("swizzle") permutes texels inside their line.  One warp-wide corner load touches
 // a small planar patch of texels, typically many (x,y) rows at the same z; without the rotation they
@@ -35,9 +35,11 @@ struct VolumeDesc {
     int gn[3], org[3];
     float own_lo[3], own_hi[3];
     int bricked;
-    int slot_shift;       // log2(SLOTS): 3 for f32x4, 4 for f16x4
+    int slot_shift;       // log2(entries per 128-byte line): 3 for f32x4, 4 for f16x4, one less with pairs
+    int pair;             // 1: every entry holds the z-pair {texel(iz), texel(min(iz+1, n-1))} (2x memory): one
+                          // 256-bit (f32x4) / 128-bit (f16x4) load fetches both z-taps of a trilinear corner row
     int row_lines;        // lines per z-row = ceil(n[2] / SLOTS)
-    int swz_x, swz_y;     // slot rotation multipliers (0, 0 = no swizzle)
+    int swz_x, swz_y, swz_z;   // slot = (swz_z*iz + swz_x*ix + swz_y*iy) mod SLOTS; swz_z odd; (0, 0, 1) = no swizzle
     float bmin[3], bmax[3];
     // fast path: voxel coordinate = world * vscale + voff  (= tc * n - 0.5)
     float vscale[3], voff[3];
@@ -53,7 +55,7 @@ struct VolumeDesc {
 
 __host__ __device__ __forceinline__ long long texel_index(const VolumeDesc &v, int ix, int iy, int iz) {
     const long long line = ((long long)ix * v.n[1] + iy) * v.row_lines + (iz >> v.slot_shift);
-    const int slot = (iz + v.swz_x * ix + v.swz_y * iy) & ((1 << v.slot_shift) - 1);
+    const int slot = (v.swz_z * iz + v.swz_x * ix + v.swz_y * iy) & ((1 << v.slot_shift) - 1);
     return (line << v.slot_shift) + slot;
 }
 
@@ -101,6 +103,8 @@ enum { CNT_SAMPLES = 0, CNT_FETCHED = 1, CNT_HIT = 2, CNT_TERM = 3, CNT_N = 4 };
 // Launchers (defined next to their kernels).
 cudaError_t launch_march(const MarchArgs &args, int n_views, bool half_texels, bool wide_index,
                          cudaStream_t stream);
+// bytes of one entry of the packed array
+__host__ __device__ __forceinline__ int entry_bytes(bool half_texels, int pair) { return (half_texels ? 8 : 16) << pair; }
 // composite.cu: sort-last compositing of pre-blend fragment colours (premultiplied rgb, alpha)
 cudaError_t launch_composite_over(const float4 *front, const float4 *back, float4 *out, size_t n_pixels,
                                   float term_alpha, cudaStream_t stream);

@@ -53,6 +53,17 @@ __device__ __forceinline__ Taps voxel_taps(float x, int n) {
     return t;
 }
 
+// z axis of the fast path.  Below the first texel centre (i = -1) both taps are texel 0 and the weight is
+// irrelevant; forcing it to 0 keeps that true for z-pair entries, whose second half is texel(i0 + 1).
+__device__ __forceinline__ Taps voxel_taps_z(float x, int n) {
+    const int i = __float2int_rd(x);
+    Taps t;
+    t.f = i < 0 ? 0.0f : x - (float)i;
+    t.i0 = max(i, 0);
+    t.i1 = min(i + 1, n - 1);
+    return t;
+}
+
 __device__ __forceinline__ float lerpf(float a, float b, float t) { return fmaf(t, b - a, a); }
 
 template <bool HALF, typename IDX>
@@ -67,15 +78,34 @@ __device__ __forceinline__ float4 load_texel(const void *base, IDX idx) {
     }
 }
 
+// One z-pair entry {texel(iz), texel(iz+1)}: a single LDG.E.128 (f16x4) or LDG.E.256 (f32x4, sm_100+).
+template <bool HALF, typename IDX>
+__device__ __forceinline__ void load_pair(const void *base, IDX idx, float4 &lo, float4 &hi) {
+    if constexpr (HALF) {
+        const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(base) + idx);
+        const float2 a = __half22float2(*reinterpret_cast<const __half2 *>(&raw.x));
+        const float2 b = __half22float2(*reinterpret_cast<const __half2 *>(&raw.y));
+        const float2 c = __half22float2(*reinterpret_cast<const __half2 *>(&raw.z));
+        const float2 d = __half22float2(*reinterpret_cast<const __half2 *>(&raw.w));
+        lo = make_float4(a.x, a.y, b.x, b.y);
+        hi = make_float4(c.x, c.y, d.x, d.y);
+    } else {
+        const char *p = reinterpret_cast<const char *>(base) + (size_t)idx * 32;
+        asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+            : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w), "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w)
+            : "l"(p));
+    }
+}
+
 struct Corner8 {
     float4 c[8];  // index = (x_tap << 2) | (y_tap << 1) | z_tap
 };
 
 // Eight corner fetches from the line/slot layout of common.cuh.  IDX is int (packed array < 2^31
-// texels) or long long.
-template <bool HALF, typename IDX, bool BRICK>
+// entries) or long long.  PAIR: four loads, each bringing both z-taps of one (x, y) row.
+template <bool HALF, typename IDX, bool BRICK, bool PAIR>
 __device__ __forceinline__ Corner8 gather(const VolumeDesc &v, const Taps &tx, const Taps &ty, const Taps &tz) {
-    constexpr int LS = HALF ? 4 : 3, SLOT_MASK = (1 << LS) - 1;
+    constexpr int LS = (HALF ? 4 : 3) - (PAIR ? 1 : 0), SLOT_MASK = (1 << LS) - 1;
     // taps are indices of the whole volume; a brick stores the sub-block that starts at v.org
     const int x0 = BRICK ? tx.i0 - v.org[0] : tx.i0, x1 = BRICK ? tx.i1 - v.org[0] : tx.i1;
     const int y0 = BRICK ? ty.i0 - v.org[1] : ty.i0, y1 = BRICK ? ty.i1 - v.org[1] : ty.i1;
@@ -86,16 +116,24 @@ __device__ __forceinline__ Corner8 gather(const VolumeDesc &v, const Taps &tx, c
     const int lz0 = z0 >> LS, lz1 = z1 >> LS;
     const int sx0 = v.swz_x * x0, sx1 = v.swz_x * x1, sy0 = v.swz_y * y0, sy1 = v.swz_y * y1;
     const int s00 = sx0 + sy0, s01 = sx0 + sy1, s10 = sx1 + sy0, s11 = sx1 + sy1;
-#define PYVR_AT(l, s, lz, iz) ((((l) + (lz)) << LS) + (IDX)(((s) + (iz)) & SLOT_MASK))
+#define PYVR_AT(l, s, lz, sz) ((((l) + (lz)) << LS) + (IDX)(((s) + (sz)) & SLOT_MASK))
+    const int q0 = v.swz_z * z0, q1 = v.swz_z * z1;
     Corner8 r;
-    r.c[0] = load_texel<HALF, IDX>(v.texels, PYVR_AT(l00, s00, lz0, z0));
-    r.c[1] = load_texel<HALF, IDX>(v.texels, PYVR_AT(l00, s00, lz1, z1));
-    r.c[2] = load_texel<HALF, IDX>(v.texels, PYVR_AT(l01, s01, lz0, z0));
-    r.c[3] = load_texel<HALF, IDX>(v.texels, PYVR_AT(l01, s01, lz1, z1));
-    r.c[4] = load_texel<HALF, IDX>(v.texels, PYVR_AT(l10, s10, lz0, z0));
-    r.c[5] = load_texel<HALF, IDX>(v.texels, PYVR_AT(l10, s10, lz1, z1));
-    r.c[6] = load_texel<HALF, IDX>(v.texels, PYVR_AT(l11, s11, lz0, z0));
-    r.c[7] = load_texel<HALF, IDX>(v.texels, PYVR_AT(l11, s11, lz1, z1));
+    if constexpr (PAIR) {
+        load_pair<HALF, IDX>(v.texels, PYVR_AT(l00, s00, lz0, q0), r.c[0], r.c[1]);
+        load_pair<HALF, IDX>(v.texels, PYVR_AT(l01, s01, lz0, q0), r.c[2], r.c[3]);
+        load_pair<HALF, IDX>(v.texels, PYVR_AT(l10, s10, lz0, q0), r.c[4], r.c[5]);
+        load_pair<HALF, IDX>(v.texels, PYVR_AT(l11, s11, lz0, q0), r.c[6], r.c[7]);
+    } else {
+        r.c[0] = load_texel<HALF, IDX>(v.texels, PYVR_AT(l00, s00, lz0, q0));
+        r.c[1] = load_texel<HALF, IDX>(v.texels, PYVR_AT(l00, s00, lz1, q1));
+        r.c[2] = load_texel<HALF, IDX>(v.texels, PYVR_AT(l01, s01, lz0, q0));
+        r.c[3] = load_texel<HALF, IDX>(v.texels, PYVR_AT(l01, s01, lz1, q1));
+        r.c[4] = load_texel<HALF, IDX>(v.texels, PYVR_AT(l10, s10, lz0, q0));
+        r.c[5] = load_texel<HALF, IDX>(v.texels, PYVR_AT(l10, s10, lz1, q1));
+        r.c[6] = load_texel<HALF, IDX>(v.texels, PYVR_AT(l11, s11, lz0, q0));
+        r.c[7] = load_texel<HALF, IDX>(v.texels, PYVR_AT(l11, s11, lz1, q1));
+    }
 #undef PYVR_AT
     return r;
 }
@@ -159,8 +197,12 @@ __device__ __forceinline__ void index_slab(float X0, float D, float lo, float hi
     }
 }
 
-template <bool STRICT, bool HALF, typename IDX, bool BRICK>
-__global__ void __launch_bounds__(CTA_THREADS)
+#ifndef PYVR_MARCH_MIN_BLOCKS
+#define PYVR_MARCH_MIN_BLOCKS 7   // 7 CTAs x 4 warps per SM <=> at most 72 registers per thread
+#endif
+
+template <bool STRICT, bool HALF, typename IDX, bool BRICK, bool PAIR>
+__global__ void __launch_bounds__(CTA_THREADS, PYVR_MARCH_MIN_BLOCKS)
 march_kernel(const __grid_constant__ MarchArgs a) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int px = blockIdx.x * TILE_W + (warp & 1) * 8 + (lane & 7);
@@ -252,8 +294,9 @@ march_kernel(const __grid_constant__ MarchArgs a) {
                         ++n_samples; ++n_fetched;
                         const Taps tx = axis_taps(tcx, vol.gn[0]), ty = axis_taps(tcy, vol.gn[1]),
                                    tz = axis_taps(tcz, vol.gn[2]);
-                        const Corner8 c8 = gather<HALF, IDX, false>(vol, tx, ty, tz);
-                        shade<true>(a, s_lut, c8, tx.f, ty.f, tz.f, acc);
+                        // (z-pair entries: below the first texel centre both taps are texel 0, so the weight is moot)
+                        const Corner8 c8 = gather<HALF, IDX, false, PAIR>(vol, tx, ty, tz);
+                        shade<true>(a, s_lut, c8, tx.f, ty.f, PAIR && tz.i1 == tz.i0 && tz.i0 == 0 ? 0.0f : tz.f, acc);
                     }
                     pxw += sx; pyw += sy; pzw += sz;
                 }
@@ -369,7 +412,7 @@ march_kernel(const __grid_constant__ MarchArgs a) {
                 while (i <= j_hi) {
                     const float fi = (float)i;
                     const float x = fmaf(fi, DX, X0), y = fmaf(fi, DY, Y0), z = fmaf(fi, DZ, Z0);
-                    tx = voxel_taps(x, vol.gn[0]); ty = voxel_taps(y, vol.gn[1]); tz = voxel_taps(z, vol.gn[2]);
+                    tx = voxel_taps(x, vol.gn[0]); ty = voxel_taps(y, vol.gn[1]); tz = voxel_taps_z(z, vol.gn[2]);
                     if (i < run_end) { have = true; break; }
                     // Cell byte (volume_pack.cu): b < 128: inactive, every cell within chessboard radius
                     // b-1 is inactive too; b >= 128: active, every cell within radius b-128 is active.
@@ -396,7 +439,7 @@ march_kernel(const __grid_constant__ MarchArgs a) {
             if (!__any_sync(0xffffffffu, have)) break;
             if (have) {
                 ++n_fetched;
-                const Corner8 c8 = gather<HALF, IDX, BRICK>(vol, tx, ty, tz);
+                const Corner8 c8 = gather<HALF, IDX, BRICK, PAIR>(vol, tx, ty, tz);
                 shade<false>(a, s_lut, c8, tx.f, ty.f, tz.f, acc);
                 if (acc.a >= a.term_alpha) {
                     terminated = i < max_last;
@@ -434,10 +477,10 @@ march_kernel(const __grid_constant__ MarchArgs a) {
     }
 }
 
-template <bool STRICT, bool HALF, typename IDX, bool BRICK>
+template <bool STRICT, bool HALF, typename IDX, bool BRICK, bool PAIR>
 cudaError_t launch_one(const MarchArgs &a, int n_views, cudaStream_t stream) {
     const size_t smem = (size_t)a.lut_size * sizeof(float4);
-    auto kern = march_kernel<STRICT, HALF, IDX, BRICK>;
+    auto kern = march_kernel<STRICT, HALF, IDX, BRICK, PAIR>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -447,26 +490,31 @@ cudaError_t launch_one(const MarchArgs &a, int n_views, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
-template <bool STRICT, bool HALF>
-cudaError_t launch_idx(const MarchArgs &a, int n_views, bool wide, cudaStream_t stream) {
-    if constexpr (!STRICT) {
-        if (a.vol.bricked)
-            return wide ? launch_one<false, HALF, long long, true>(a, n_views, stream)
-                        : launch_one<false, HALF, int, true>(a, n_views, stream);
-    }
-    return wide ? launch_one<STRICT, HALF, long long, false>(a, n_views, stream)
-                : launch_one<STRICT, HALF, int, false>(a, n_views, stream);
+template <bool HALF, bool PAIR>
+cudaError_t launch_fast(const MarchArgs &a, int n_views, bool wide, cudaStream_t stream) {
+    if (a.vol.bricked)
+        return wide ? launch_one<false, HALF, long long, true, PAIR>(a, n_views, stream)
+                    : launch_one<false, HALF, int, true, PAIR>(a, n_views, stream);
+    return wide ? launch_one<false, HALF, long long, false, PAIR>(a, n_views, stream)
+                : launch_one<false, HALF, int, false, PAIR>(a, n_views, stream);
 }
 
 }  // namespace
 
 cudaError_t launch_march(const MarchArgs &a, int n_views, bool half_texels, bool wide_index, cudaStream_t stream) {
-    // bricks are marched by the fast path only (the STRICT twin of the oracle has no notion of ownership)
-    const bool strict = (a.flags & PYVR_FLAG_STRICT) != 0 && !a.vol.bricked;
-    if (strict) return half_texels ? launch_idx<true, true>(a, n_views, wide_index, stream)
-                                   : launch_idx<true, false>(a, n_views, wide_index, stream);
-    return half_texels ? launch_idx<false, true>(a, n_views, wide_index, stream)
-                       : launch_idx<false, false>(a, n_views, wide_index, stream);
+    const bool pair = a.vol.pair != 0;
+    // bricks are marched by the fast path only (the STRICT twin of the oracle has no notion of ownership);
+    // STRICT is a test mode and always uses 64-bit indices
+    if ((a.flags & PYVR_FLAG_STRICT) != 0 && !a.vol.bricked) {
+        if (half_texels) return pair ? launch_one<true, true, long long, false, true>(a, n_views, stream)
+                                     : launch_one<true, true, long long, false, false>(a, n_views, stream);
+        return pair ? launch_one<true, false, long long, false, true>(a, n_views, stream)
+                    : launch_one<true, false, long long, false, false>(a, n_views, stream);
+    }
+    if (half_texels) return pair ? launch_fast<true, true>(a, n_views, wide_index, stream)
+                                 : launch_fast<true, false>(a, n_views, wide_index, stream);
+    return pair ? launch_fast<false, true>(a, n_views, wide_index, stream)
+                : launch_fast<false, false>(a, n_views, wide_index, stream);
 }
 
 }  // namespace pyvr

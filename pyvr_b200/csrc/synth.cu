@@ -96,15 +96,27 @@ normals_pack_kernel(const float *__restrict__ slab, VolumeDesc v, int gsize, int
         const float g2 = diff1(slab[at - 1], c, slab[at + 1], gz, gsize);
         const float norm = sqrtf(g0 * g0 + g1 * g1 + g2 * g2) + 1e-8f;
         const float nx = g0 / norm, nyv = g1 / norm, nzv = g2 / norm;
-        const long long dst = texel_index(v, lx0 + ixs, iy, iz);
-        if constexpr (HALF) {
-            __half2 lo = __floats2half2_rn(c, nx), hi = __floats2half2_rn(nyv, nzv);
-            uint2 raw;
-            raw.x = *reinterpret_cast<unsigned *>(&lo);
-            raw.y = *reinterpret_cast<unsigned *>(&hi);
-            reinterpret_cast<uint2 *>(const_cast<void *>(v.texels))[dst] = raw;
+        // plain layout: one slot.  z-pair layout: this texel is the first half of entry(iz), the second half
+        // of entry(iz - 1) and, at the top of the block, also the second half of its own entry.
+        long long dsts[3];
+        int n_dst = 0;
+        if (!v.pair) {
+            dsts[n_dst++] = texel_index(v, lx0 + ixs, iy, iz);
         } else {
-            reinterpret_cast<float4 *>(const_cast<void *>(v.texels))[dst] = make_float4(c, nx, nyv, nzv);
+            dsts[n_dst++] = texel_index(v, lx0 + ixs, iy, iz) * 2;
+            if (iz > 0) dsts[n_dst++] = texel_index(v, lx0 + ixs, iy, iz - 1) * 2 + 1;
+            if (iz == nz - 1) dsts[n_dst++] = texel_index(v, lx0 + ixs, iy, iz) * 2 + 1;
+        }
+        for (int d = 0; d < n_dst; ++d) {
+            if constexpr (HALF) {
+                __half2 lo = __floats2half2_rn(c, nx), hi = __floats2half2_rn(nyv, nzv);
+                uint2 raw;
+                raw.x = *reinterpret_cast<unsigned *>(&lo);
+                raw.y = *reinterpret_cast<unsigned *>(&hi);
+                reinterpret_cast<uint2 *>(const_cast<void *>(v.texels))[dsts[d]] = raw;
+            } else {
+                reinterpret_cast<float4 *>(const_cast<void *>(v.texels))[dsts[d]] = make_float4(c, nx, nyv, nzv);
+            }
         }
     }
 }
@@ -119,7 +131,7 @@ unpack_texels_kernel(VolumeDesc v, float *__restrict__ scalar, float *__restrict
         const int iz = (int)(flat % v.n[2]);
         const long long r = flat / v.n[2];
         const int iy = (int)(r % v.n[1]), ix = (int)(r / v.n[1]);
-        const long long at = texel_index(v, ix, iy, iz);
+        const long long at = texel_index(v, ix, iy, iz) << v.pair;
         float4 t;
         if constexpr (HALF) {
             const uint2 raw = reinterpret_cast<const uint2 *>(v.texels)[at];

@@ -26,30 +26,36 @@ pack_texels_kernel(const float *__restrict__ scalar, const float *__restrict__ n
         const int iz = (int)(flat % nz);
         const long long rest = flat / nz;
         const int iy = (int)(rest % ny), ix = (int)(rest / ny);
-        const float s = scalar[flat];
-        float a, b, c;
-        if (normals) {
-            a = normals[3 * flat + 0]; b = normals[3 * flat + 1]; c = normals[3 * flat + 2];
-        } else {
-            a = s; b = 0.0f; c = 0.0f;
-        }
         const long long at = texel_index(v, ix, iy, iz);
-        if constexpr (HALF) {
-            __half2 lo = __floats2half2_rn(s, a), hi = __floats2half2_rn(b, c);
-            uint2 raw;
-            raw.x = *reinterpret_cast<unsigned *>(&lo);
-            raw.y = *reinterpret_cast<unsigned *>(&hi);
-            reinterpret_cast<uint2 *>(const_cast<void *>(v.texels))[at] = raw;
-        } else {
-            reinterpret_cast<float4 *>(const_cast<void *>(v.texels))[at] = make_float4(s, a, b, c);
+        // z-pair entries hold this texel and its upper z neighbour (clamped at the top of the block)
+        for (int e = 0; e <= v.pair; ++e) {
+            const long long src = e && iz + 1 < nz ? flat + 1 : flat;
+            const float s = scalar[src];
+            float a, b, c;
+            if (normals) {
+                a = normals[3 * src + 0]; b = normals[3 * src + 1]; c = normals[3 * src + 2];
+            } else {
+                a = s; b = 0.0f; c = 0.0f;
+            }
+            const long long dst = (at << v.pair) + e;
+            if constexpr (HALF) {
+                __half2 lo = __floats2half2_rn(s, a), hi = __floats2half2_rn(b, c);
+                uint2 raw;
+                raw.x = *reinterpret_cast<unsigned *>(&lo);
+                raw.y = *reinterpret_cast<unsigned *>(&hi);
+                reinterpret_cast<uint2 *>(const_cast<void *>(v.texels))[dst] = raw;
+            } else {
+                reinterpret_cast<float4 *>(const_cast<void *>(v.texels))[dst] = make_float4(s, a, b, c);
+            }
         }
     }
 }
 
+// scalar of entry idx (the first texel of a z-pair entry)
 template <bool HALF>
-__device__ __forceinline__ float load_scalar(const void *base, long long idx) {
-    if constexpr (HALF) return __half2float(reinterpret_cast<const __half *>(base)[4 * idx]);
-    else return reinterpret_cast<const float *>(base)[4 * idx];
+__device__ __forceinline__ float load_scalar(const void *base, long long idx, int pair) {
+    if constexpr (HALF) return __half2float(reinterpret_cast<const __half *>(base)[(4 * idx) << pair]);
+    else return reinterpret_cast<const float *>(base)[(4 * idx) << pair];
 }
 
 // One warp per macrocell: min/max of the scalar over texels [8c, min(8c+8, n-1)]^3 -- the cell's own
@@ -71,7 +77,7 @@ cell_minmax_kernel(VolumeDesc v, float2 *__restrict__ out) {
         for (int t = lane; t < wx * wy * wz; t += 32) {
             const int dz = t % wz, dy = (t / wz) % wy, dx = t / (wz * wy);
             const long long at = texel_index(v, x0 + dx, y0 + dy, z0 + dz);
-            const float s = load_scalar<HALF>(v.texels, at);
+            const float s = load_scalar<HALF>(v.texels, at, v.pair);
             // NaN voxels: keep the cell active by poisoning the range
             if (s != s) { lo = -INFINITY; hi = INFINITY; }
             lo = fminf(lo, s); hi = fmaxf(hi, s);

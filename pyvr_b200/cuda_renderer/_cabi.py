@@ -100,11 +100,12 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("PYVR_CUDA_LIB") or LIB_PATH      # override: A/B builds of the same ABI
+    if not os.path.exists(path):
         raise RuntimeError(
-            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(nvcc, sm_100a).  pyvr_b200 has no CPU fallback.")
-    handle = ctypes.CDLL(LIB_PATH)
+    handle = ctypes.CDLL(path)
     for name, (restype, argtypes) in SYMBOLS.items():
         fn = getattr(handle, name)
         fn.restype, fn.argtypes = restype, argtypes

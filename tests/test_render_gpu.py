@@ -292,3 +292,31 @@ def test_honor_config_termination_is_opt_in(c1):
     assert_parity(ref_like, want)                           # default: 0.99, like the shader
     early, stats = _render_gpu(vol, cam, light, cfg, lut, 128, 128, honor_config_termination=True)
     assert early[..., 3].max() < ref_like[..., 3].max()
+
+
+@pytest.mark.parametrize("name", ["fuel", "hydrogen"])
+@pytest.mark.parametrize("view", ["iso", "front"])
+def test_c2_vti_volumes_high_quality_camera_linked_light(tmp_path, golden_dir, name, view):
+    """BASELINE config 2: the reference's example volumes through the .vti loader (bounds +-1, normals from the
+    stencil kernel, huge exactly-zero background => the normalize(0) NaN path), 1024x1024, high_quality,
+    camera-linked light.  The oracle renders every 4th row to stay within seconds."""
+    import json
+
+    from pyvr_b200.dataloaders import load_vtk_volume
+    from vti_writer import write_vti
+
+    vols = np.load(os.path.join(golden_dir, "vti_volumes.npz"))
+    meta = json.load(open(os.path.join(golden_dir, "vti_meta.json")))
+    path = write_vti(tmp_path / f"{name}.vti", {"Scalars_": vols[name].astype(np.float32).ravel()}, meta[name]["dims_xyz"])
+    vol = load_vtk_volume(path)                                  # normals on the GPU (K2)
+    assert vol.has_normals and np.array_equal(vol.normals, oracle.normals(vol.data))
+    assert not np.isnan(vol.normals).any() and (np.abs(vol.normals).sum(axis=-1) == 0).mean() > 0.5
+    cam = Camera.isometric_view(distance=3.0) if view == "iso" else Camera.front_view(distance=3.0)
+    light = Light.camera_linked()
+    light.update_from_camera(cam)
+    cfg, lut, size = RenderConfig.high_quality(), viridis_lut(0.0, 0.3), 1024
+    rows = (1, size, 4)
+    want, _, counters = oracle.render(vol, cam, light, cfg, lut, size, size, rows=rows)
+    got, stats = _render_gpu(vol, cam, light, cfg, lut, size, size)
+    assert stats["rays_hit"] > 300000 and got.any()
+    assert_parity(got[rows[0]::rows[2]], want[rows[0]::rows[2]])
