@@ -57,9 +57,11 @@ def parse_args():
     ap.add_argument("--views-per-step", type=int, default=12)
     ap.add_argument("--texels", default="f32", choices=["f32", "f16"])
     ap.add_argument("--no-ess", action="store_true", help="disable empty-space skipping")
+    ap.add_argument("--hwtex", action="store_true", help="sample through the texture unit (hardware trilinear)")
     ap.add_argument("--layout", default=None, choices=["linear", "swizzle"])
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--no-alternatives", action="store_true", help="skip the f16 / hwtex side measurements")
     return ap.parse_args()
 
 
@@ -229,6 +231,7 @@ def workload_config(args, stride_note=None):
         "texels": "f32x4 (16 B/voxel)" if args.texels == "f32" else "f16x4 (8 B/voxel)",
         "l2_policy": f"inputs larger than L2 (packed volume {args.size ** 3 * (16 if args.texels == 'f32' else 8) / 2 ** 30:.2f} GiB vs 126 MB L2), no flush",
         "empty_space_skipping": not args.no_ess,
+        "sampling": "texture unit, hardware trilinear (8-bit weights)" if getattr(args, "hwtex", False) else "binary32 software trilinear",
     }
     if stride_note:
         cfg["sample"] = stride_note
@@ -282,7 +285,8 @@ def main():
     vol = Volume(data=data, normals=normals, min_bounds=np.array([-1, -1, -1], np.float32),
                  max_bounds=np.array([1, 1, 1], np.float32))
     renderer = VolumeRenderer(args.width, args.height, config=config, light=light, device=local_rank,
-                              texel_format=args.texels, empty_space_skipping=not args.no_ess)
+                              texel_format=args.texels, empty_space_skipping=not args.no_ess,
+                              hardware_filtering=args.hwtex)
     renderer.load_volume(vol)
     renderer.set_lut(lut)
     stream = torch.cuda.Stream()   # non-default: the library treats stream 0 as "use the context's own stream"
@@ -359,6 +363,33 @@ def main():
     e2e_value = sum_over_ranks(float(e2e_samples)) / (e2e_ms * 1e-3) / 1e9
     checksum = int(pinned.array[::4099].astype(np.uint64).sum())
 
+    # ---------------- alternatives (N = 1 only): same views, other texel storage / sampler, device-resident.
+    # Not the headline: the headline is binary32 texels + binary32 software trilinear (the north star's
+    # primary path); these are the configurations the north star lists as allowed when within tolerance.
+    alternatives = {}
+    if world == 1 and not args.no_alternatives:
+        for name, kw in (("f16x4 texels, software trilinear", dict(texel_format="f16")),
+                         ("f16x4 texels, texture-unit trilinear (hwtex)", dict(texel_format="f16", hardware_filtering=True))):
+            alt = VolumeRenderer(args.width, args.height, config=config, light=light, device=local_rank,
+                                 empty_space_skipping=not args.no_ess, **kw)
+            alt.load_volume(vol)
+            alt.set_lut(lut)
+            alt.set_stream(stream.cuda_stream)
+            for s_ in range(args.warmup):
+                alt.render_batch(views=views[s_], device_ptr=d_frames.data_ptr())
+            torch.cuda.synchronize()
+            e0.record(stream)
+            alt_samples = 0
+            for s_ in range(args.warmup, total_steps):
+                alt.render_batch(views=views[s_], device_ptr=d_frames.data_ptr())
+                alt_samples += alt.stats["samples"]
+            e1.record(stream)
+            torch.cuda.synchronize()
+            alt_ms = e0.elapsed_time(e1)
+            alternatives[name] = {"value": alt_samples / (alt_ms * 1e-3) / 1e9, "unit": "Gsamples/s",
+                                  "frames_per_s": args.steps * per_step / (alt_ms * 1e-3)}
+            alt.close()
+
     if rank == 0:
         bytes_per_sample = BYTES_PER_SAMPLE_F32 if args.texels == "f32" else BYTES_PER_SAMPLE_F16
         peak, peak_src = measured_peak_gbs()
@@ -401,6 +432,7 @@ def main():
             "clocks": clocks.summary(),
             "normals_kernel": {"ms": normals_ms, "GB/s": args.size ** 3 * 16 / (normals_ms * 1e-3) / 1e9,
                                "frac_of_hbm_peak": args.size ** 3 * 16 / (normals_ms * 1e-3) / 1e9 / peak},
+            "alternatives": alternatives,
             "setup_s": setup_s,
         }
         if not args.skip_cpu_baseline and world == 1:

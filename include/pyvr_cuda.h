@@ -47,6 +47,11 @@ typedef enum {
                                     no empty-space skipping (used to compare against the oracle bit for bit) */
 #define PYVR_FLAG_ESS      0x2u  /* macrocell empty-space skipping (exact: skips only zero contributions) */
 #define PYVR_FLAG_NO_BLEND 0x4u  /* RGBA8 output holds (C, A) instead of the reference's blended (C*A, A*A) */
+#define PYVR_FLAG_HWTEX    0x8u  /* sample through the texture unit (3-D CUDA array, hardware trilinear filter with
+                                    8-bit fixed-point weights) instead of binary32 software trilinear.  What the
+                                    reference's own sampler3D does on a real GPU; NOT bit-comparable with the oracle,
+                                    offered only because it passes the stated tolerance (tests/test_hwtex_gpu.py).
+                                    Ignored with PYVR_FLAG_STRICT. */
 
 typedef struct pyvr_ctx pyvr_ctx;
 

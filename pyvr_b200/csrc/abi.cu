@@ -71,6 +71,8 @@ struct pyvr_ctx {
     int shard_rank = 0, shard_count = 1;   // image-space tile sharding (pyvr_cuda_set_pixel_shard)
     int pair_option = -1;   // z-pair entries: -1 auto (when the doubled array stays under kPairBudget), 0 off, 1 on
     bool use_pair = false;  // decided per upload
+    cudaArray_t tex_array = nullptr;        // PYVR_FLAG_HWTEX: built on first use from the packed texels
+    cudaTextureObject_t tex_obj = 0;
 
     // transfer function
     float4 *lut = nullptr;
@@ -210,7 +212,58 @@ int classify_cells(pyvr_ctx *c) {
     return PYVR_OK;
 }
 
+void free_texture(pyvr_ctx *c) {
+    if (c->tex_obj) cudaDestroyTextureObject(c->tex_obj);
+    if (c->tex_array) cudaFreeArray(c->tex_array);
+    c->tex_obj = 0;
+    c->tex_array = nullptr;
+}
+
+// 3-D CUDA array + texture object over the stored block: width = z (memory-fastest), height = y, depth = x;
+// LINEAR filter, CLAMP addressing, unnormalised coordinates -- the sampler state of manager.py:98-101.
+// Filled slab by slab through a <= 256 MiB staging buffer.
+int ensure_texture(pyvr_ctx *c) {
+    if (c->tex_obj || !c->have_volume) return PYVR_OK;
+    const VolumeDesc &v = c->vol;
+    const size_t tb = c->half_texels ? 8 : 16;
+    cudaChannelFormatDesc desc = c->half_texels ? cudaCreateChannelDescHalf4() : cudaCreateChannelDesc<float4>();
+    CU(cudaMalloc3DArray(&c->tex_array, &desc, make_cudaExtent(v.n[2], v.n[1], v.n[0])));
+    const size_t plane = (size_t)v.n[1] * v.n[2] * tb;
+    size_t planes = ((size_t)256 << 20) / plane;
+    if (planes < 1) planes = 1;
+    if (planes > (size_t)v.n[0]) planes = v.n[0];
+    void *stage = nullptr;
+    cudaError_t e = cudaMalloc(&stage, planes * plane);
+    for (int x0 = 0; e == cudaSuccess && x0 < v.n[0]; x0 += (int)planes) {
+        const int nx = v.n[0] - x0 < (int)planes ? v.n[0] - x0 : (int)planes;
+        e = launch_linearize_texels(v, c->half_texels, x0, nx, stage, c->stream);
+        cudaMemcpy3DParms p = {};
+        p.srcPtr = make_cudaPitchedPtr(stage, (size_t)v.n[2] * tb, v.n[2], v.n[1]);
+        p.dstArray = c->tex_array;
+        p.dstPos = make_cudaPos(0, 0, x0);
+        p.extent = make_cudaExtent(v.n[2], v.n[1], nx);
+        p.kind = cudaMemcpyDeviceToDevice;
+        if (e == cudaSuccess) e = cudaMemcpy3DAsync(&p, c->stream);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(stage);
+    if (e == cudaSuccess) {
+        cudaResourceDesc rd = {};
+        rd.resType = cudaResourceTypeArray;
+        rd.res.array.array = c->tex_array;
+        cudaTextureDesc td = {};
+        td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+        td.filterMode = cudaFilterModeLinear;
+        td.readMode = cudaReadModeElementType;
+        td.normalizedCoords = 0;
+        e = cudaCreateTextureObject(&c->tex_obj, &rd, &td, nullptr);
+    }
+    if (e != cudaSuccess) { free_texture(c); CU(e); }
+    return PYVR_OK;
+}
+
 void free_volume(pyvr_ctx *c) {
+    free_texture(c);
     cudaFree(c->texels); c->texels = nullptr;
     cudaFree(c->cell_minmax); c->cell_minmax = nullptr;
     cudaFree(c->cell_dist); c->cell_dist = nullptr;
@@ -271,7 +324,12 @@ MarchArgs make_args(const pyvr_ctx *c) {
 // Launch the march for `n` views already resident in c->d_views[first..], timed with events.
 int march(pyvr_ctx *c, int first, int n, uchar4 *out8, float4 *out_acc, size_t ev_pair,
           const float4 *in_acc = nullptr) {
+    if ((c->params.flags & PYVR_FLAG_HWTEX) && !(c->params.flags & PYVR_FLAG_STRICT)) {
+        int rc = ensure_texture(c);
+        if (rc != PYVR_OK) return rc;
+    }
     MarchArgs a = make_args(c);
+    a.tex = c->tex_obj;
     a.views = c->d_views + first;
     a.out8 = out8;
     a.out_acc = out_acc;

@@ -62,6 +62,7 @@ __host__ __device__ __forceinline__ long long texel_index(const VolumeDesc &v, i
 struct MarchArgs {
     VolumeDesc vol;
     const pyvr_view *views;        // device array, indexed by blockIdx.z
+    cudaTextureObject_t tex;       // PYVR_FLAG_HWTEX: the same texels as a 3-D array (width = z), linear filter, clamp
     const float4 *lut;             // device, lut_size entries
     int lut_size;
     int width, height;
@@ -122,6 +123,8 @@ cudaError_t launch_cell_classify(const float2 *cell_minmax, const VolumeDesc &vo
 // synth.cu: analytic volume -> packed texels (scalar + normals), slab by slab through `scratch`
 cudaError_t launch_synth_volume(const VolumeDesc &vol, bool half_texels, int shape, int size, float *scratch,
                                 size_t scratch_floats, cudaStream_t stream);
+// raw texels of x-planes [x0, x0 + nx) in plain [x][y][z] order (staging for the 3-D CUDA array)
+cudaError_t launch_linearize_texels(const VolumeDesc &vol, bool half_texels, int x0, int nx, void *dst, cudaStream_t stream);
 cudaError_t launch_unpack_texels(const VolumeDesc &vol, bool half_texels, float *scalar, float *normals,
                                  cudaStream_t stream);
 cudaError_t launch_normals(const float *in, float *out, int n0, int n1, int n2, cudaStream_t stream);

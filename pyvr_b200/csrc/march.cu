@@ -185,6 +185,24 @@ __device__ __forceinline__ void shade(const MarchArgs &a, const float4 *s_lut, c
     acc.a = fmaf(t, alpha, acc.a);
 }
 
+// Same for a texel the texture unit has already filtered (PYVR_FLAG_HWTEX), fast arithmetic.
+__device__ __forceinline__ void shade_filtered(const MarchArgs &a, const float4 *s_lut, const float4 &t, Accum &acc) {
+    const Taps tl = axis_taps(t.x, a.lut_size);
+    const float4 l0 = s_lut[tl.i0], l1 = s_lut[tl.i1];
+    const float alpha_tf = lerpf(l0.w, l1.w, tl.f);
+    if (alpha_tf == 0.0f) return;
+    const float alpha = 1.0f - ex2_approx(alpha_tf * a.exp2_scale);
+    const float cr = lerpf(l0.x, l1.x, tl.f), cg = lerpf(l0.y, l1.y, tl.f), cb = lerpf(l0.z, l1.z, tl.f);
+    const float inv = rsqrtf(fmaf(t.w, t.w, fmaf(t.z, t.z, t.y * t.y)));
+    const float ndotl = fmaf(t.w * inv, a.ldir[2], fmaf(t.z * inv, a.ldir[1], t.y * inv * a.ldir[0]));
+    const float light = fmaf(a.diffuse, fmaxf(ndotl, 0.0f), a.ambient);
+    const float tr = 1.0f - acc.a;
+    acc.r = fmaf(tr, cr * light * alpha, acc.r);
+    acc.g = fmaf(tr, cg * light * alpha, acc.g);
+    acc.b = fmaf(tr, cb * light * alpha, acc.b);
+    acc.a = fmaf(tr, alpha, acc.a);
+}
+
 // Index interval on which lo <= X0 + i*D <= hi, intersected into [enter, exit].
 __device__ __forceinline__ void index_slab(float X0, float D, float lo, float hi, float &enter, float &exit) {
     if (D != 0.0f) {
@@ -201,7 +219,7 @@ __device__ __forceinline__ void index_slab(float X0, float D, float lo, float hi
 #define PYVR_MARCH_MIN_BLOCKS 7   // 7 CTAs x 4 warps per SM <=> at most 72 registers per thread
 #endif
 
-template <bool STRICT, bool HALF, typename IDX, bool BRICK, bool PAIR>
+template <bool STRICT, bool HALF, typename IDX, bool BRICK, bool PAIR, bool TEX>
 __global__ void __launch_bounds__(CTA_THREADS, PYVR_MARCH_MIN_BLOCKS)
 march_kernel(const __grid_constant__ MarchArgs a) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -407,20 +425,27 @@ march_kernel(const __grid_constant__ MarchArgs a) {
         int run_end = ess ? i : 0x7fffffff;   // first index not known to lie in an active run of cells
         while (true) {
             Taps tx, ty, tz;
+            float px_ = 0.0f, py_ = 0.0f, pz_ = 0.0f;   // TEX: the sample's voxel coordinate
             bool have = false;
             if (alive) {
                 while (i <= j_hi) {
                     const float fi = (float)i;
                     const float x = fmaf(fi, DX, X0), y = fmaf(fi, DY, Y0), z = fmaf(fi, DZ, Z0);
-                    tx = voxel_taps(x, vol.gn[0]); ty = voxel_taps(y, vol.gn[1]); tz = voxel_taps_z(z, vol.gn[2]);
+                    if constexpr (TEX) {
+                        px_ = x; py_ = y; pz_ = z;
+                    } else {
+                        tx = voxel_taps(x, vol.gn[0]); ty = voxel_taps(y, vol.gn[1]); tz = voxel_taps_z(z, vol.gn[2]);
+                    }
                     if (i < run_end) { have = true; break; }
                     // Cell byte (volume_pack.cu): b < 128: inactive, every cell within chessboard radius
                     // b-1 is inactive too; b >= 128: active, every cell within radius b-128 is active.
                     // Either way the ray may run to the faces of that cube of cells: whole steps that stay
                     // inside it (and inside the volume) on every axis, conservative by 0.01 step; a zero
                     // direction component never exits.
-                    const int cx = (BRICK ? tx.i0 - vol.org[0] : tx.i0) >> 3, cy = (BRICK ? ty.i0 - vol.org[1] : ty.i0) >> 3,
-                              cz = (BRICK ? tz.i0 - vol.org[2] : tz.i0) >> 3;
+                    const int ix0 = TEX ? max(__float2int_rd(x), 0) : tx.i0, iy0 = TEX ? max(__float2int_rd(y), 0) : ty.i0,
+                              iz0 = TEX ? max(__float2int_rd(z), 0) : tz.i0;
+                    const int cx = (BRICK ? ix0 - vol.org[0] : ix0) >> 3, cy = (BRICK ? iy0 - vol.org[1] : iy0) >> 3,
+                              cz = (BRICK ? iz0 - vol.org[2] : iz0) >> 3;
                     const int b = __ldg(vol.cell_dist + (cx * vol.ncell[1] + cy) * vol.ncell[2] + cz);
                     const bool active = b >= 128;
                     const int r = active ? b - 128 : b - 1;
@@ -439,8 +464,17 @@ march_kernel(const __grid_constant__ MarchArgs a) {
             if (!__any_sync(0xffffffffu, have)) break;
             if (have) {
                 ++n_fetched;
-                const Corner8 c8 = gather<HALF, IDX, BRICK, PAIR>(vol, tx, ty, tz);
-                shade<false>(a, s_lut, c8, tx.f, ty.f, tz.f, acc);
+                if constexpr (TEX) {
+                    // texel centres sit at integer + 0.5 in unnormalised texture space; width = z
+                    const float u = pz_ + 0.5f - (BRICK ? (float)vol.org[2] : 0.0f);
+                    const float w2 = py_ + 0.5f - (BRICK ? (float)vol.org[1] : 0.0f);
+                    const float w3 = px_ + 0.5f - (BRICK ? (float)vol.org[0] : 0.0f);
+                    const float4 t = tex3D<float4>(a.tex, u, w2, w3);
+                    shade_filtered(a, s_lut, t, acc);
+                } else {
+                    const Corner8 c8 = gather<HALF, IDX, BRICK, PAIR>(vol, tx, ty, tz);
+                    shade<false>(a, s_lut, c8, tx.f, ty.f, tz.f, acc);
+                }
                 if (acc.a >= a.term_alpha) {
                     terminated = i < max_last;
                     last = i;
@@ -477,10 +511,10 @@ march_kernel(const __grid_constant__ MarchArgs a) {
     }
 }
 
-template <bool STRICT, bool HALF, typename IDX, bool BRICK, bool PAIR>
+template <bool STRICT, bool HALF, typename IDX, bool BRICK, bool PAIR, bool TEX = false>
 cudaError_t launch_one(const MarchArgs &a, int n_views, cudaStream_t stream) {
     const size_t smem = (size_t)a.lut_size * sizeof(float4);
-    auto kern = march_kernel<STRICT, HALF, IDX, BRICK, PAIR>;
+    auto kern = march_kernel<STRICT, HALF, IDX, BRICK, PAIR, TEX>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -511,6 +545,9 @@ cudaError_t launch_march(const MarchArgs &a, int n_views, bool half_texels, bool
         return pair ? launch_one<true, false, long long, false, true>(a, n_views, stream)
                     : launch_one<true, false, long long, false, false>(a, n_views, stream);
     }
+    if ((a.flags & PYVR_FLAG_HWTEX) != 0 && a.tex != 0)   // the texture object hides texel format and layout
+        return a.vol.bricked ? launch_one<false, false, int, true, false, true>(a, n_views, stream)
+                             : launch_one<false, false, int, false, false, true>(a, n_views, stream);
     if (half_texels) return pair ? launch_fast<true, true>(a, n_views, wide_index, stream)
                                  : launch_fast<true, false>(a, n_views, wide_index, stream);
     return pair ? launch_fast<false, true>(a, n_views, wide_index, stream)

@@ -146,6 +146,20 @@ unpack_texels_kernel(VolumeDesc v, float *__restrict__ scalar, float *__restrict
     }
 }
 
+// Raw copy of the stored texels of x-planes [x0, x0 + nx) into plain [x][y][z] order.
+template <typename T>
+__global__ void __launch_bounds__(256)
+linearize_texels_kernel(VolumeDesc v, int x0, int nx, T *__restrict__ dst) {
+    const long long total = (long long)nx * v.n[1] * v.n[2];
+    for (long long flat = (long long)blockIdx.x * blockDim.x + threadIdx.x; flat < total;
+         flat += (long long)gridDim.x * blockDim.x) {
+        const int iz = (int)(flat % v.n[2]);
+        const long long r = flat / v.n[2];
+        const int iy = (int)(r % v.n[1]), ix = (int)(r / v.n[1]);
+        dst[flat] = reinterpret_cast<const T *>(v.texels)[texel_index(v, x0 + ix, iy, iz) << v.pair];
+    }
+}
+
 inline int grid_for(long long work) {
     long long g = (work + 255) / 256;
     const long long cap = 148LL * 16;
@@ -170,6 +184,13 @@ cudaError_t launch_synth_volume(const VolumeDesc &vol, bool half_texels, int sha
         if (half_texels) normals_pack_kernel<true><<<grid_for(work), 256, 0, stream>>>(scratch, vol, size, lx0, nxs, sy, sz);
         else normals_pack_kernel<false><<<grid_for(work), 256, 0, stream>>>(scratch, vol, size, lx0, nxs, sy, sz);
     }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_linearize_texels(const VolumeDesc &vol, bool half_texels, int x0, int nx, void *dst, cudaStream_t stream) {
+    const long long total = (long long)nx * vol.n[1] * vol.n[2];
+    if (half_texels) linearize_texels_kernel<uint2><<<grid_for(total), 256, 0, stream>>>(vol, x0, nx, reinterpret_cast<uint2 *>(dst));
+    else linearize_texels_kernel<float4><<<grid_for(total), 256, 0, stream>>>(vol, x0, nx, reinterpret_cast<float4 *>(dst));
     return cudaGetLastError();
 }
 

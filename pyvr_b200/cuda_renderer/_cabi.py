@@ -19,7 +19,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libpyvr_cuda.so")
 ABI_VERSION = 2
 IPC_HANDLE_BYTES = 64
 TEXEL_F32X4, TEXEL_F16X4 = 0, 1
-FLAG_STRICT, FLAG_ESS, FLAG_NO_BLEND = 0x1, 0x2, 0x4
+FLAG_STRICT, FLAG_ESS, FLAG_NO_BLEND, FLAG_HWTEX = 0x1, 0x2, 0x4, 0x8
 SHAPES = {"sphere": 0, "torus": 1, "double_sphere": 2}
 
 # name -> (restype, argtypes); every symbol include/pyvr_cuda.h declares

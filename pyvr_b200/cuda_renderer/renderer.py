@@ -41,7 +41,8 @@ def _is_a(obj, own_cls, name: str) -> bool:
 class CudaVolumeRenderer:
     def __init__(self, width=512, height=512, config=None, light=None, *, device: int = 0,
                  texel_format: str = "f32", strict: bool = False,
-                 empty_space_skipping: bool = True, honor_config_termination: bool = False):
+                 empty_space_skipping: bool = True, honor_config_termination: bool = False,
+                 hardware_filtering: bool = False):
         """
         Args:
             width, height, config, light: as the reference (balanced preset / ``Light.default()``).
@@ -49,6 +50,9 @@ class CudaVolumeRenderer:
             texel_format: ``"f32"`` ({s,nx,ny,nz} binary32, parity configs) or ``"f16"``.
             strict: reference-faithful arithmetic (slow; used to pin the kernel to the oracle).
             empty_space_skipping: exact macrocell skipping (pixels unchanged).
+            hardware_filtering: sample through the texture unit (3-D CUDA array, hardware trilinear
+                filter with 8-bit weights) instead of binary32 software trilinear.  Within the stated
+                tolerance of the oracle but not bit-comparable with it; off by default.
             honor_config_termination: NON-PARITY opt-in -- stop rays at
                 ``config.opacity_threshold`` (or never, if ``early_ray_termination`` is off)
                 instead of the shader's literal 0.99.
@@ -78,6 +82,7 @@ class CudaVolumeRenderer:
         self._strict = bool(strict)
         self._ess = bool(empty_space_skipping)
         self._honor_termination = bool(honor_config_termination)
+        self._hwtex = bool(hardware_filtering)
         self._lib = _cabi.lib()
         self._ctx = ctypes.c_void_p()
         _cabi.check(self._lib.pyvr_cuda_create(self.device, int(width), int(height), ctypes.byref(self._ctx)))
@@ -330,6 +335,8 @@ class CudaVolumeRenderer:
             flags |= _cabi.FLAG_STRICT
         elif self._ess:
             flags |= _cabi.FLAG_ESS
+        if self._hwtex and not self._strict:
+            flags |= _cabi.FLAG_HWTEX
         p.flags = flags
         _cabi.check(self._lib.pyvr_cuda_set_params(self._ctx, ctypes.byref(p)))
 
