@@ -420,42 +420,38 @@ march_kernel(const __grid_constant__ MarchArgs a) {
         // lanes active in the gather).
         const bool ess = (a.flags & PYVR_FLAG_ESS) && vol.cell_dist != nullptr;
         const float hx = (float)vol.gn[0] - 0.5f, hy = (float)vol.gn[1] - 0.5f, hz = (float)vol.gn[2] - 0.5f;
-        const float rDX = 1.0f / DX, rDY = 1.0f / DY, rDZ = 1.0f / DZ;
+        // Per-ray constants of the cell walk.  Along an axis the ray leaves a cube of cells [c - r, c + r]
+        // through the face at voxel 8*(c + r + 1) (moving up) or 8*(c - r) (moving down):
+        //   face = 8*c + r*fstep + fbase,  fstep = +-8,  fbase = 8 or 0 (plus the brick origin);
+        // a zero direction component is treated as "up" with an infinite reciprocal, i.e. it never exits.
+        const float rDX = DX != 0.0f ? 1.0f / DX : 3.0e38f, rDY = DY != 0.0f ? 1.0f / DY : 3.0e38f,
+                    rDZ = DZ != 0.0f ? 1.0f / DZ : 3.0e38f;
+        const int ogx = BRICK ? vol.org[0] : 0, ogy = BRICK ? vol.org[1] : 0, ogz = BRICK ? vol.org[2] : 0;
+        const int fstep_x = DX < 0.0f ? -8 : 8, fstep_y = DY < 0.0f ? -8 : 8, fstep_z = DZ < 0.0f ? -8 : 8;
+        const int fbase_x = (DX < 0.0f ? 0 : 8) + ogx, fbase_y = (DY < 0.0f ? 0 : 8) + ogy, fbase_z = (DZ < 0.0f ? 0 : 8) + ogz;
         const int max_last = a.max_steps - 1;
         int run_end = ess ? i : 0x7fffffff;   // first index not known to lie in an active run of cells
         while (true) {
-            Taps tx, ty, tz;
-            float px_ = 0.0f, py_ = 0.0f, pz_ = 0.0f;   // TEX: the sample's voxel coordinate
             bool have = false;
             if (alive) {
                 while (i <= j_hi) {
-                    const float fi = (float)i;
-                    const float x = fmaf(fi, DX, X0), y = fmaf(fi, DY, Y0), z = fmaf(fi, DZ, Z0);
-                    if constexpr (TEX) {
-                        px_ = x; py_ = y; pz_ = z;
-                    } else {
-                        tx = voxel_taps(x, vol.gn[0]); ty = voxel_taps(y, vol.gn[1]); tz = voxel_taps_z(z, vol.gn[2]);
-                    }
                     if (i < run_end) { have = true; break; }
                     // Cell byte (volume_pack.cu): b < 128: inactive, every cell within chessboard radius
                     // b-1 is inactive too; b >= 128: active, every cell within radius b-128 is active.
                     // Either way the ray may run to the faces of that cube of cells: whole steps that stay
-                    // inside it (and inside the volume) on every axis, conservative by 0.01 step; a zero
-                    // direction component never exits.
-                    const int ix0 = TEX ? max(__float2int_rd(x), 0) : tx.i0, iy0 = TEX ? max(__float2int_rd(y), 0) : ty.i0,
-                              iz0 = TEX ? max(__float2int_rd(z), 0) : tz.i0;
-                    const int cx = (BRICK ? ix0 - vol.org[0] : ix0) >> 3, cy = (BRICK ? iy0 - vol.org[1] : iy0) >> 3,
-                              cz = (BRICK ? iz0 - vol.org[2] : iz0) >> 3;
-                    const int b = __ldg(vol.cell_dist + (cx * vol.ncell[1] + cy) * vol.ncell[2] + cz);
+                    // inside it (and inside the volume) on every axis, conservative by 0.01 step.
+                    const float fi = (float)i;
+                    const float x = fmaf(fi, DX, X0), y = fmaf(fi, DY, Y0), z = fmaf(fi, DZ, Z0);
+                    const int lx = max(__float2int_rd(x), 0) - ogx, ly = max(__float2int_rd(y), 0) - ogy,
+                              lz = max(__float2int_rd(z), 0) - ogz;     // lower tap, local to the stored block
+                    const int b = __ldg(vol.cell_dist + ((lx >> 3) * vol.ncell[1] + (ly >> 3)) * vol.ncell[2] + (lz >> 3));
                     const bool active = b >= 128;
-                    const int r = active ? b - 128 : b - 1;
-                    const int ox = BRICK ? vol.org[0] : 0, oy = BRICK ? vol.org[1] : 0, oz = BRICK ? vol.org[2] : 0;
-                    const float ex = ((DX > 0.0f ? fminf((float)(ox + 8 * (cx + r) + 8), hx) : fmaxf((float)(ox + 8 * (cx - r)), -0.5f)) - x) * rDX;
-                    const float ey = ((DY > 0.0f ? fminf((float)(oy + 8 * (cy + r) + 8), hy) : fmaxf((float)(oy + 8 * (cy - r)), -0.5f)) - y) * rDY;
-                    const float ez = ((DZ > 0.0f ? fminf((float)(oz + 8 * (cz + r) + 8), hz) : fmaxf((float)(oz + 8 * (cz - r)), -0.5f)) - z) * rDZ;
-                    const float tmin = fminf(fminf(DX != 0.0f ? ex : 3.0e38f, DY != 0.0f ? ey : 3.0e38f),
-                                             DZ != 0.0f ? ez : 3.0e38f);
-                    const int stay = max((int)fminf(floorf(tmin - 0.01f), 1.0e6f), 1);
+                    const int r = (b & 127) - (active ? 0 : 1);
+                    const float fx = fminf(fmaxf((float)((lx & ~7) + r * fstep_x + fbase_x), -0.5f), hx);
+                    const float fy = fminf(fmaxf((float)((ly & ~7) + r * fstep_y + fbase_y), -0.5f), hy);
+                    const float fz = fminf(fmaxf((float)((lz & ~7) + r * fstep_z + fbase_z), -0.5f), hz);
+                    const float tmin = fminf(fminf((fx - x) * rDX, (fy - y) * rDY), (fz - z) * rDZ);
+                    const int stay = min(max(__float2int_rd(tmin - 0.01f), 1), 1 << 24);
                     if (active) { run_end = i + stay; have = true; break; }
                     i += stay;
                 }
@@ -464,14 +460,14 @@ march_kernel(const __grid_constant__ MarchArgs a) {
             if (!__any_sync(0xffffffffu, have)) break;
             if (have) {
                 ++n_fetched;
+                const float fi = (float)i;
+                const float x = fmaf(fi, DX, X0), y = fmaf(fi, DY, Y0), z = fmaf(fi, DZ, Z0);
                 if constexpr (TEX) {
                     // texel centres sit at integer + 0.5 in unnormalised texture space; width = z
-                    const float u = pz_ + 0.5f - (BRICK ? (float)vol.org[2] : 0.0f);
-                    const float w2 = py_ + 0.5f - (BRICK ? (float)vol.org[1] : 0.0f);
-                    const float w3 = px_ + 0.5f - (BRICK ? (float)vol.org[0] : 0.0f);
-                    const float4 t = tex3D<float4>(a.tex, u, w2, w3);
+                    const float4 t = tex3D<float4>(a.tex, z + 0.5f - (float)ogz, y + 0.5f - (float)ogy, x + 0.5f - (float)ogx);
                     shade_filtered(a, s_lut, t, acc);
                 } else {
+                    const Taps tx = voxel_taps(x, vol.gn[0]), ty = voxel_taps(y, vol.gn[1]), tz = voxel_taps_z(z, vol.gn[2]);
                     const Corner8 c8 = gather<HALF, IDX, BRICK, PAIR>(vol, tx, ty, tz);
                     shade<false>(a, s_lut, c8, tx.f, ty.f, tz.f, acc);
                 }
