@@ -280,14 +280,27 @@ def main():
     from pyvr_b200.cuda_renderer import VolumeRenderer, _cabi
 
     t_setup = time.perf_counter()
-    data, light, config, lut = scene(args.size)
-    normals, normals_ms = _cabi.compute_normals_host(data, device=local_rank, return_ms=True)   # K2
-    vol = Volume(data=data, normals=normals, min_bounds=np.array([-1, -1, -1], np.float32),
-                 max_bounds=np.array([1, 1, 1], np.float32))
-    renderer = VolumeRenderer(args.width, args.height, config=config, light=light, device=local_rank,
-                              texel_format=args.texels, empty_space_skipping=not args.no_ess,
-                              hardware_filtering=args.hwtex)
-    renderer.load_volume(vol)
+    renderer_kw = dict(device=local_rank, texel_format=args.texels, empty_space_skipping=not args.no_ess,
+                       hardware_filtering=args.hwtex)
+    if world == 1:
+        # host pipeline, as a user of the reference would: create_sample_volume -> compute_normal_volume (K2 on
+        # the GPU) -> Volume -> load_volume.  The host arrays also feed the CPU baseline.
+        data, light, config, lut = scene(args.size)
+        normals, normals_ms = _cabi.compute_normals_host(data, device=local_rank, return_ms=True)   # K2
+        vol = Volume(data=data, normals=normals, min_bounds=np.array([-1, -1, -1], np.float32),
+                     max_bounds=np.array([1, 1, 1], np.float32))
+        renderer = VolumeRenderer(args.width, args.height, config=config, light=light, **renderer_kw)
+        renderer.load_volume(vol)
+    else:
+        # N > 1: every rank builds the SAME texels on its own device (synth.cu; identical to the host pipeline,
+        # tests/test_synth_gpu.py) instead of N processes each holding ~6 GB of host temporaries
+        from pyvr_b200 import (ColorTransferFunction, Light, OpacityTransferFunction, RenderConfig, build_rgba_lut)
+
+        data = normals = vol = None
+        light, config = Light.directional([1, -1, 0]), RenderConfig.high_quality()
+        lut = build_rgba_lut(ColorTransferFunction.from_colormap("viridis"), OpacityTransferFunction.linear(0.0, 0.1))
+        renderer = VolumeRenderer(args.width, args.height, config=config, light=light, **renderer_kw)
+        normals_ms = renderer.generate_volume(args.size, "double_sphere", (-1, -1, -1), (1, 1, 1))
     renderer.set_lut(lut)
     stream = torch.cuda.Stream()   # non-default: the library treats stream 0 as "use the context's own stream"
     renderer.set_stream(stream.cuda_stream)
@@ -367,7 +380,7 @@ def main():
     # Not the headline: the headline is binary32 texels + binary32 software trilinear (the north star's
     # primary path); these are the configurations the north star lists as allowed when within tolerance.
     alternatives = {}
-    if world == 1 and not args.no_alternatives:
+    if world == 1 and not args.no_alternatives and not args.hwtex and args.texels == "f32":
         for name, kw in (("f16x4 texels, software trilinear", dict(texel_format="f16")),
                          ("f16x4 texels, texture-unit trilinear (hwtex)", dict(texel_format="f16", hardware_filtering=True))):
             alt = VolumeRenderer(args.width, args.height, config=config, light=light, device=local_rank,
@@ -430,8 +443,10 @@ def main():
                         "fraction of the HBM copy rate exceeds 1; see `l1` for the binding unit",
             },
             "clocks": clocks.summary(),
-            "normals_kernel": {"ms": normals_ms, "GB/s": args.size ** 3 * 16 / (normals_ms * 1e-3) / 1e9,
-                               "frac_of_hbm_peak": args.size ** 3 * 16 / (normals_ms * 1e-3) / 1e9 / peak},
+            "normals_kernel": ({"ms": normals_ms, "GB/s": args.size ** 3 * 16 / (normals_ms * 1e-3) / 1e9,
+                                "frac_of_hbm_peak": args.size ** 3 * 16 / (normals_ms * 1e-3) / 1e9 / peak,
+                                "algorithmic_bytes_per_voxel": 16} if world == 1 else
+                               {"device_generation_ms": normals_ms}),
             "alternatives": alternatives,
             "setup_s": setup_s,
         }
