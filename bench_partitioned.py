@@ -91,6 +91,7 @@ def run(args, rank, world, local_rank):
     setup_s = time.perf_counter() - t0
 
     frame = torch.zeros((n_pixels, 4), dtype=torch.uint8, device="cuda")
+    frame_ptr = frame.data_ptr()
     pinned = _cabi.PinnedBuffer(n_pixels * 4)
 
     def barrier():
@@ -114,7 +115,7 @@ def run(args, rank, world, local_rank):
 
     def step(read_back=False):
         """One frame.  Returns this rank's pyvr_stats."""
-        nonlocal frame
+        nonlocal frame, frame_ptr
         if read_back:
             renderer.set_camera(camera)                      # camera uniforms travel host -> device again
         if session is not None:
@@ -123,14 +124,14 @@ def run(args, rank, world, local_rank):
             piece_range, piece = session.composite(position)
             out = session.gather_rgba8(piece_range, piece)
             if out is not None:
-                frame = out
+                frame_ptr = out if isinstance(out, int) else out.data_ptr()
         else:
             renderer.render_to_device(frame.data_ptr())
             st = renderer.stats
             if world > 1:
                 mg.reduce_tile_frames(frame, dst=0)
         if read_back and rank == 0:
-            _cabi.check(_cabi.lib().pyvr_cuda_memcpy(local_rank, pinned.array.ctypes.data, ctypes.c_void_p(frame.data_ptr()),
+            _cabi.check(_cabi.lib().pyvr_cuda_memcpy(local_rank, pinned.array.ctypes.data, ctypes.c_void_p(frame_ptr),
                                                      n_pixels * 4, 2, ctypes.c_void_p(stream.cuda_stream)))
         return st
 

@@ -306,7 +306,8 @@ class SortLastSession:
         self._over = over
         self._peers = {}
         self.image = None          # float32 (n_pixels, 4)
-        self._own = None
+        self._own = self._frame = None
+        self._gather_out = self._gather_in = self._gather_frame = None
         if exchange == "p2p":
             self._setup_p2p()
         elif exchange != "nccl":
@@ -316,11 +317,32 @@ class SortLastSession:
     def _setup_p2p(self):
         from .cuda_renderer import _cabi
 
+        # two IPC-shared buffers per rank: the float4 partial image and the RGBA8 frame (only rank `dst`'s
+        # frame is ever written: every rank finalises its piece straight into it across NVLink)
         self._own = _cabi.DeviceBuffer(self.n_pixels * 16, self.device)
+        self._frame = _cabi.DeviceBuffer(self.n_pixels * 4, self.device)
         handles = [None] * self.world
-        self.dist.all_gather_object(handles, self._own.ipc_handle(), group=self.group)
+        self.dist.all_gather_object(handles, (self._own.ipc_handle(), self._frame.ipc_handle()), group=self.group)
+        self._handles = handles
         for step in self.plan:
-            self._peers[step.partner] = _cabi.PeerBuffer(handles[step.partner], self.device)
+            self._peers[step.partner] = _cabi.PeerBuffer(handles[step.partner][0], self.device)
+        self._frame_peers = {}
+        self._fence_t = self.torch.zeros(1, dtype=self.torch.float32, device=f"cuda:{self.device}")
+
+    def _fence(self):
+        """Device-side barrier in stream order: the tiny all-reduce of rank A cannot complete before every
+        rank's kernel has started, i.e. before everything the ranks enqueued earlier has finished.  No host
+        synchronisation."""
+        self.dist.all_reduce(self._fence_t, group=self.group)
+
+    def _dst_frame_ptr(self, dst: int) -> int:
+        from .cuda_renderer import _cabi
+
+        if dst == self.rank:
+            return self._frame.ptr
+        if dst not in self._frame_peers:
+            self._frame_peers[dst] = _cabi.PeerBuffer(self._handles[dst][1], self.device)
+        return self._frame_peers[dst].ptr
 
     def image_ptr(self) -> int:
         """Device pointer the renderer writes its partial image to (``render_accum_to_device``)."""
@@ -374,53 +396,67 @@ class SortLastSession:
     def _composite_p2p(self, cam):
         from .cuda_renderer import _cabi
 
-        torch, dist = self.torch, self.dist
+        torch = self.torch
         stream = torch.cuda.current_stream().cuda_stream
         for step in self.plan:
             # the partner's current image must be complete before it is read, and nobody may still be reading
             # the range this rank is about to overwrite
-            torch.cuda.synchronize()
-            dist.barrier(group=self.group)
+            self._fence()
             klo, khi = step.keep
             mine = self._own.ptr + klo * 16
             theirs = self._peers[step.partner].ptr + klo * 16
             front, back = (mine, theirs) if self._i_am_front(step, cam) else (theirs, mine)
             # fused transfer + merge: the kernel loads the partner's half across NVLink and writes in place
             _cabi.composite_over(self.device, front, back, mine, khi - klo, self.term, stream)
-        torch.cuda.synchronize()
-        dist.barrier(group=self.group)
         lo, hi = self.plan[-1].keep if self.plan else (0, self.n_pixels)
         return (lo, hi), self._own.ptr + lo * 16
 
     # -- final frame -----------------------------------------------------------------------------
     def gather_rgba8(self, piece_range, piece, flags: int = 0, dst: int = 0):
-        """Finalise this rank's piece to RGBA8 and gather the frame on rank ``dst`` (``None`` elsewhere)."""
+        """Finalise this rank's piece to RGBA8 and assemble the frame on rank ``dst``.  Returns, on ``dst``, the
+        frame as a uint8 ``(n_pixels, 4)`` tensor (``"nccl"``) or as a raw device pointer (``"p2p"``: the
+        IPC-shared frame buffer); ``None`` on the other ranks."""
         from .cuda_renderer import _cabi
 
         torch, dist = self.torch, self.dist
         lo, hi = piece_range
         n = hi - lo
+        if self.exchange == "p2p":
+            # every rank writes its finalised piece straight into rank dst's frame (peer stores over NVLink);
+            # the closing fence tells dst the frame is complete and everyone that its image may be reused
+            _cabi.finalize_rgba8(self.device, piece, self._dst_frame_ptr(dst) + lo * 4, n, flags,
+                                 torch.cuda.current_stream().cuda_stream)
+            self._fence()
+            return self._frame.ptr if self.rank == dst else None
         per = -(-self.n_pixels // self.world)            # pieces differ by at most one pixel: pad to the largest
-        out = torch.zeros((per, 4), dtype=torch.uint8, device=f"cuda:{self.device}")
+        if self._gather_out is None:
+            self._gather_out = torch.zeros((per, 4), dtype=torch.uint8, device=f"cuda:{self.device}")
+            self._gather_in = [torch.empty_like(self._gather_out) for _ in range(self.world)] if self.rank == dst else None
+            self._gather_frame = torch.empty((self.n_pixels, 4), dtype=torch.uint8, device=self._gather_out.device)
+        out = self._gather_out
         ptr = piece if isinstance(piece, int) else piece.contiguous().data_ptr()
         _cabi.finalize_rgba8(self.device, ptr, out.data_ptr(), n, flags, torch.cuda.current_stream().cuda_stream)
-        gathered = [torch.empty_like(out) for _ in range(self.world)] if self.rank == dst else None
+        gathered = self._gather_in
         dist.gather(out, gathered, dst=dst, group=self.group)
         if self.rank != dst:
             return None
-        frame = torch.empty((self.n_pixels, 4), dtype=torch.uint8, device=out.device)
+        frame = self._gather_frame
         for r in range(self.world):
             rlo, rhi = final_piece(r, self.world, self.n_pixels)
             frame[rlo:rhi] = gathered[r][:rhi - rlo]
         return frame
 
     def close(self):
-        for p in self._peers.values():
+        if self.exchange == "p2p":
+            self.torch.cuda.synchronize()
+            self.dist.barrier(group=self.group)       # nobody unmaps while a peer may still touch the memory
+        for p in list(self._peers.values()) + list(getattr(self, "_frame_peers", {}).values()):
             p.close()
-        self._peers = {}
-        if self._own is not None:
-            self._own.close()
-            self._own = None
+        self._peers, self._frame_peers = {}, {}
+        for buf in (self._own, self._frame):
+            if buf is not None:
+                buf.close()
+        self._own = self._frame = None
 
 
 def reduce_tile_frames(frame, dst: int = 0, group=None):

@@ -6,6 +6,7 @@ un-partitioned render and to the oracle.  The tests at the bottom spawn one proc
 CUDA-IPC peer path) and are skipped on a single-GPU box.
 """
 
+import ctypes
 import dataclasses
 import os
 import socket
@@ -286,6 +287,11 @@ def _dist_worker(rank, world, port, out_dir, exchange):
                 r.render_accum_to_device(session.image_ptr())
                 piece_range, piece = session.composite(position)
                 frame = session.gather_rgba8(piece_range, piece)
+                if isinstance(frame, int):      # p2p: raw pointer of the IPC-shared frame buffer on rank 0
+                    torch.cuda.synchronize()
+                    host = np.empty(W * H * 4, np.uint8)
+                    _cabi.check(_cabi.lib().pyvr_cuda_memcpy(rank, host.ctypes.data, ctypes.c_void_p(frame), W * H * 4, 2, None))
+                    frame = torch.from_numpy(host)
             samples = torch.tensor([r.stats["samples"]], dtype=torch.int64, device="cuda")
             dist.all_reduce(samples)
             # exact relay on the same bricks
