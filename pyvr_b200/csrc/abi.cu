@@ -36,7 +36,8 @@ int fail(int code, const char *fmt, ...) {
     } while (0)
 
 constexpr size_t kPairBudget = (size_t)40 << 30;   // auto z-pair layout up to 40 GiB of packed texels
-constexpr int kRing = 3;  // device frame slots used to overlap march and device->host copies
+constexpr int kRing = 3;   // device slots used to overlap march and device->host copies
+constexpr int kSlotViews = 4;   // views marched per launch on the host-output path (one slot = kSlotViews frames)
 
 struct DeviceGuard {
     int prev = -1;
@@ -86,7 +87,7 @@ struct pyvr_ctx {
     // frame resources
     pyvr_view *d_views = nullptr;
     int views_cap = 0;
-    uchar4 *frames = nullptr;      // kRing frames
+    uchar4 *frames = nullptr;      // kRing slots of kSlotViews frames
     float4 *accum = nullptr;       // one frame, allocated on demand
     unsigned long long *d_counters = nullptr;
     unsigned long long *h_counters = nullptr;  // pinned
@@ -401,7 +402,7 @@ int pyvr_cuda_create(int device, int width, int height, pyvr_ctx **out_ctx) {
     c->params.flags = PYVR_FLAG_ESS;
     cudaError_t e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaMalloc(&c->frames, frame_pixels(c) * sizeof(uchar4) * kRing);
+    if (e == cudaSuccess) e = cudaMalloc(&c->frames, frame_pixels(c) * sizeof(uchar4) * kRing * kSlotViews);
     if (e == cudaSuccess) e = cudaMalloc(&c->d_counters, sizeof(unsigned long long) * CNT_N);
     if (e == cudaSuccess) e = cudaMallocHost(&c->h_counters, sizeof(unsigned long long) * CNT_N);
     for (int i = 0; i < kRing && e == cudaSuccess; ++i) {
@@ -759,18 +760,21 @@ int pyvr_cuda_render_batch(pyvr_ctx *c, const pyvr_view *views, int n, uint8_t *
             if (rc != PYVR_OK) return rc;
         }
     } else {
-        // ring of device frames: march(k) overlaps the device->host copy of frame k-1
-        rc = ensure_events(c, (size_t)n);
+        // ring of device slots: the march of group g overlaps the device->host copy of group g-1.  A group is
+        // up to kSlotViews views in one launch (fewer launch tails than one launch per view).
+        const int groups = (n + kSlotViews - 1) / kSlotViews;
+        rc = ensure_events(c, (size_t)groups);
         if (rc != PYVR_OK) return rc;
-        for (int k = 0; k < n; ++k) {
-            const int slot = k % kRing;
-            if (k >= kRing) CU(cudaStreamWaitEvent(c->stream, c->slot_copied[slot], 0));
-            uchar4 *frame = c->frames + (size_t)slot * frame_pixels(c);
-            rc = march(c, k, 1, frame, nullptr, pairs++);
+        for (int g = 0; g < groups; ++g) {
+            const int first = g * kSlotViews, m = n - first < kSlotViews ? n - first : kSlotViews;
+            const int slot = g % kRing;
+            if (g >= kRing) CU(cudaStreamWaitEvent(c->stream, c->slot_copied[slot], 0));
+            uchar4 *frames = c->frames + (size_t)slot * kSlotViews * frame_pixels(c);
+            rc = march(c, first, m, frames, nullptr, pairs++);
             if (rc != PYVR_OK) return rc;
             CU(cudaEventRecord(c->slot_rendered[slot], c->stream));
             CU(cudaStreamWaitEvent(c->copy_stream, c->slot_rendered[slot], 0));
-            CU(cudaMemcpyAsync(out + (size_t)k * frame_bytes, frame, frame_bytes, cudaMemcpyDeviceToHost, c->copy_stream));
+            CU(cudaMemcpyAsync(out + (size_t)first * frame_bytes, frames, frame_bytes * m, cudaMemcpyDeviceToHost, c->copy_stream));
             CU(cudaEventRecord(c->slot_copied[slot], c->copy_stream));
         }
         CU(cudaStreamSynchronize(c->copy_stream));

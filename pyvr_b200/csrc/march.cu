@@ -24,7 +24,12 @@
 namespace pyvr {
 namespace {
 
-constexpr int TILE_W = 16, TILE_H = 8, CTA_THREADS = TILE_W * TILE_H;
+// Warp tile WARP_W x WARP_H pixels (one ray per lane), CTA = 2 x 2 warps.
+#ifndef PYVR_WARP_W
+#define PYVR_WARP_W 8
+#endif
+constexpr int WARP_W = PYVR_WARP_W, WARP_H = 32 / WARP_W;
+constexpr int TILE_W = 2 * WARP_W, TILE_H = 2 * WARP_H, CTA_THREADS = TILE_W * TILE_H;
 
 struct Taps {
     int i0, i1;
@@ -223,8 +228,8 @@ template <bool STRICT, bool HALF, typename IDX, bool BRICK, bool PAIR, bool TEX>
 __global__ void __launch_bounds__(CTA_THREADS, PYVR_MARCH_MIN_BLOCKS)
 march_kernel(const __grid_constant__ MarchArgs a) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int px = blockIdx.x * TILE_W + (warp & 1) * 8 + (lane & 7);
-    const int py = blockIdx.y * TILE_H + (warp >> 1) * 4 + (lane >> 3);
+    const int px = blockIdx.x * TILE_W + (warp & 1) * WARP_W + (lane % WARP_W);
+    const int py = blockIdx.y * TILE_H + (warp >> 1) * WARP_H + (lane / WARP_W);
     const bool in_image = px < a.width && py < a.height;
 
     // image-space sharding: a CTA whose 64x64 tile group belongs to another rank only clears its pixels
