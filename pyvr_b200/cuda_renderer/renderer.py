@@ -84,6 +84,7 @@ class CudaVolumeRenderer:
         self._honor_termination = bool(honor_config_termination)
         self._hwtex = bool(hardware_filtering)
         self._lib = _cabi.lib()
+        self._staging = None
         self._ctx = ctypes.c_void_p()
         _cabi.check(self._lib.pyvr_cuda_create(self.device, int(width), int(height), ctypes.byref(self._ctx)))
         self._push_params()
@@ -93,6 +94,9 @@ class CudaVolumeRenderer:
         ctx, self._ctx = getattr(self, "_ctx", None), None
         if ctx:
             self._lib.pyvr_cuda_destroy(ctx)
+        staging, self._staging = getattr(self, "_staging", None), None
+        if staging is not None:
+            staging.close()
 
     def __del__(self):
         try:
@@ -155,9 +159,10 @@ class CudaVolumeRenderer:
 
     def render(self) -> bytes:
         """Raw RGBA8 pixels, ``width*height*4`` bytes, bottom row first."""
-        out = np.empty(self.width * self.height * 4, dtype=np.uint8)
-        _cabi.check(self._lib.pyvr_cuda_render(self._ctx, out.ctypes.data, 0))
-        return out.tobytes()
+        if self._staging is None:      # page-locked read-back target: full PCIe rate, one copy into the bytes object
+            self._staging = _cabi.PinnedBuffer(self.width * self.height * 4)
+        _cabi.check(self._lib.pyvr_cuda_render(self._ctx, self._staging.array.ctypes.data, 0))
+        return self._staging.array.tobytes()
 
     def render_to_pil(self, data=None):
         from PIL import Image
