@@ -23,20 +23,20 @@ PY
 # the driver's own command lines first
 timeout 900 python bench.py > $OUT/${TAG}_bench_default.json 2> $OUT/${TAG}_bench_default.err; summ $OUT/${TAG}_bench_default.json "driver default"
 timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/${TAG}_bench_reference.json 2> $OUT/${TAG}_bench_reference.err; tail -c 600 $OUT/${TAG}_bench_reference.json
-for variant in "--no-ess" "--layout linear --no-ess" "--texels f16" "--texels f16 --no-ess"; do
+for variant in "--no-ess" "--layout linear --no-ess" "--texels f16" "--texels f16 --no-ess" "--texels f16 --hwtex" "--hwtex"; do
   name=$(echo "bench$variant" | tr -d ' -')
   timeout 600 python bench.py --steps 3 --warmup 3 --views-per-step 6 --skip-cpu-baseline $variant > $OUT/${TAG}_${name}.json 2> $OUT/${TAG}_${name}.err
   summ $OUT/${TAG}_${name}.json "$variant"
 done
 # ncu: launch list of a short default run, then one full capture of the march kernel
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/${TAG}_launches.csv \
-    python bench.py --steps 2 --warmup 3 --views-per-step 12 --skip-cpu-baseline > $OUT/${TAG}_ncu_launch.log 2>&1
+    python bench.py --steps 2 --warmup 3 --views-per-step 12 --skip-cpu-baseline --no-alternatives > $OUT/${TAG}_ncu_launch.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:march_kernel -s 1 -c 1 -f -o $OUT/${TAG}_march \
     python bench.py --steps 1 --warmup 1 --views-per-step 1 --skip-cpu-baseline > $OUT/${TAG}_ncu_full.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:march_kernel -s 1 -c 1 -f -o $OUT/${TAG}_march_noess \
     python bench.py --steps 1 --warmup 1 --views-per-step 1 --skip-cpu-baseline --no-ess > $OUT/${TAG}_ncu_full_noess.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:march_kernel -s 1 -c 1 -f -o $OUT/${TAG}_march_f16_noess \
-    python bench.py --steps 1 --warmup 1 --views-per-step 1 --skip-cpu-baseline --no-ess --texels f16 > $OUT/${TAG}_ncu_full_f16_noess.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:march_kernel -s 1 -c 1 -f -o $OUT/${TAG}_march_hwtex16 \
+    python bench.py --steps 1 --warmup 1 --views-per-step 1 --skip-cpu-baseline --texels f16 --hwtex > $OUT/${TAG}_ncu_full_hwtex16.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:normals -c 1 -f -o $OUT/${TAG}_normals \
     python bench.py --steps 1 --warmup 1 --views-per-step 1 --skip-cpu-baseline > $OUT/${TAG}_ncu_normals.log 2>&1
 ls -la $OUT | tail -30
