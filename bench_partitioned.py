@@ -71,7 +71,7 @@ def run(args, rank, world, local_rank):
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     renderer = VolumeRenderer(width, height, config=config, light=light, device=local_rank, texel_format=texels,
-                              empty_space_skipping=not args.no_ess)
+                              empty_space_skipping=not args.no_ess, hardware_filtering=args.hwtex)
     renderer.set_stream(stream.cuda_stream)
     t0 = time.perf_counter()
     shape = (args.size,) * 3
@@ -186,7 +186,8 @@ def run(args, rank, world, local_rank):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": name, "texels": "f16x4 (8 B/voxel)" if texels == "f16" else "f32x4 (16 B/voxel)",
                        "l2_policy": f"inputs larger than L2 (packed block {voxels * (8 if texels == 'f16' else 16) / 2 ** 30:.1f} GiB per GPU), no flush",
-                       "empty_space_skipping": not args.no_ess},
+                       "empty_space_skipping": not args.no_ess,
+                       "sampling": "texture unit, hardware trilinear (8-bit weights)" if args.hwtex else "binary32 software trilinear"},
             "frames_per_s": args.steps / (ms * 1e-3), "samples_per_frame": all_samples / args.steps,
             "e2e": {"value": all_samples / (e2e_ms * 1e-3) / 1e9, "unit": "Gsamples/s",
                     "frames_per_s": args.steps / (e2e_ms * 1e-3),

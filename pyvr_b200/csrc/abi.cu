@@ -35,7 +35,7 @@ int fail(int code, const char *fmt, ...) {
                         "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
-constexpr size_t kPairBudget = (size_t)40 << 30;   // auto z-pair layout up to 40 GiB of packed texels
+constexpr double kPairBudget = 0.8;   // auto z-pair layout while the doubled array fits in this share of free HBM
 constexpr int kRing = 3;   // device slots used to overlap march and device->host copies
 constexpr int kSlotViews = 4;   // views marched per launch on the host-output path (one slot = kSlotViews frames)
 
@@ -163,7 +163,9 @@ void inverse4_f32(const float *m, float *o) {
 // z-pair layout (common.cuh) for this upload?
 void choose_pair(pyvr_ctx *c, const int local[3]) {
     const size_t doubled = (size_t)local[0] * local[1] * local[2] * (c->half_texels ? 8 : 16) * 2;
-    c->use_pair = c->pair_option < 0 ? doubled <= kPairBudget : c->pair_option != 0;
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) free_b = 0;   // called after the old volume was freed
+    c->use_pair = c->pair_option < 0 ? (double)doubled <= kPairBudget * (double)free_b : c->pair_option != 0;
 }
 
 // local[3] = stored texel counts along world x, y, z; global/org/own_* = NULL for a whole volume.
