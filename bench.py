@@ -91,24 +91,48 @@ def step_view_indices(step, rank, world, per_step):
 
 
 class ClockSampler:
-    """Samples nvidia-smi SM clocks / throttle reasons of one GPU during the timed region."""
+    """Samples SM clocks / throttle reasons of one GPU during the timed region: NVML in-process every 5 ms
+    (nvidia_ml_py), falling back to polling the nvidia-smi binary every 200 ms."""
 
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    NVML_BITS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index):
         self.index, self.rows, self._stop, self._thread = index, [], threading.Event(), None
+        self.source, self._nvml, self._handle, self.sm_max = "nvidia-smi", None, None, None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[index]) if visible and visible.split(",")[index].isdigit() else index
+            self._handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self._handle, pynvml.NVML_CLOCK_SM))
+            self._nvml, self.source = pynvml, "nvml"
+        except Exception:
+            self._nvml = None
 
     def _run(self):
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
-                if out.returncode == 0 and out.stdout.strip():
-                    self.rows.append([c.strip() for c in out.stdout.strip().split(",")])
+                if self._nvml is not None:
+                    mhz = float(self._nvml.nvmlDeviceGetClockInfo(self._handle, self._nvml.NVML_CLOCK_SM))
+                    try:
+                        mask = int(self._nvml.nvmlDeviceGetCurrentClocksEventReasons(self._handle))
+                    except Exception:
+                        mask = int(self._nvml.nvmlDeviceGetCurrentClocksThrottleReasons(self._handle))
+                    self.rows.append([mhz, self.sm_max] + [bool(mask & self.NVML_BITS[n]) for n in self.NAMES])
+                else:
+                    out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                    if out.returncode == 0 and out.stdout.strip():
+                        c = [x.strip() for x in out.stdout.strip().split(",")]
+                        self.rows.append([float(c[0]), float(c[1])] + [x.lower().startswith("active") for x in c[2:6]])
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(0.005 if self._nvml is not None else 0.2)
 
     def __enter__(self):
         self._thread = threading.Thread(target=self._run, daemon=True)
@@ -121,12 +145,11 @@ class ClockSampler:
 
     def summary(self):
         if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]),
-                "reasons": reasons, "samples": len(self.rows)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"]}
+        sm = sorted(r[0] for r in self.rows)
+        reasons = [n for i, n in enumerate(self.NAMES) if any(r[2 + i] for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": self.rows[0][1], "reasons": reasons,
+                "samples": len(self.rows), "source": self.source}
 
 
 def measured_peak_gbs():

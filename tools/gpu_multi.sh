@@ -1,10 +1,10 @@
 #!/bin/bash
 # Multi-GPU session: distributed tests + headline scaling point + C4/C5 lines.  Usage: bash tools/gpu_multi.sh N TAG
-N=${1:-8}; TAG=${2:-r01m}
+N=${1:-8}; TAG=${2:-r01m}; WHICH=${3:-all}
 OUT=gpurun_out; mkdir -p $OUT
 T="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 nvidia-smi --query-gpu=index,name,memory.total --format=csv,noheader | head -$N > $OUT/${TAG}_gpus.txt; nproc >> $OUT/${TAG}_gpus.txt; free -g | head -2 >> $OUT/${TAG}_gpus.txt
-timeout 600 python -m pytest tests/test_sort_last_gpu.py -m gpu -q --tb=short -k across_processes 2>&1 | tail -5
+[ "$WHICH" = all ] && timeout 600 python -m pytest tests/test_sort_last_gpu.py -m gpu -q --tb=short -k across_processes 2>&1 | tail -5
 run() { name=$1; shift; timeout 600 $T --master-port $((29600 + RANDOM % 300)) bench.py --gpus $N "$@" > $OUT/${TAG}_$name.json 2> $OUT/${TAG}_$name.err
   tail -1 $OUT/${TAG}_$name.json | python -c "
 import json,sys
@@ -16,5 +16,6 @@ except Exception as e:
 "; }
 run c3 --steps 6 --warmup 3
 run c4 --workload c4 --steps 4 --warmup 2
-run c5_p2p --workload c5 --exchange p2p --steps 4 --warmup 2
-run c5_nccl --workload c5 --exchange nccl --steps 4 --warmup 2
+[ "$WHICH" = all ] && run c5_p2p --workload c5 --exchange p2p --steps 4 --warmup 2
+[ "$WHICH" = all ] && run c5_nccl --workload c5 --exchange nccl --steps 4 --warmup 2
+true
