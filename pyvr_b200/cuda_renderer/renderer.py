@@ -293,6 +293,24 @@ class CudaVolumeRenderer:
         """Pre-blend fragment colours (``width*height`` float4) into a device buffer: a partial image."""
         _cabi.check(self._lib.pyvr_cuda_render_accum(self._ctx, ctypes.c_void_p(device_ptr), 1))
 
+    def render_tensor(self, cameras=None, out=None):
+        """Zero-copy device output: the current view -- or, with ``cameras``, one
+        frame per camera -- as a ``torch.uint8`` tensor ``([n,] height, width, 4)`` on this renderer's device.
+        Nothing crosses PCIe except the view parameters; row 0 is the bottom row, as in ``render()``."""
+        import torch
+
+        n = None if cameras is None else len(cameras)
+        shape = (self.height, self.width, 4) if n is None else (n, self.height, self.width, 4)
+        if out is None:
+            out = torch.empty(shape, dtype=torch.uint8, device=f"cuda:{self.device}")
+        if tuple(out.shape) != shape or out.dtype != torch.uint8 or not out.is_contiguous() or out.device.index != self.device:
+            raise ValueError(f"out must be a contiguous uint8 CUDA tensor of shape {shape} on device {self.device}")
+        if n is None:
+            _cabi.check(self._lib.pyvr_cuda_render(self._ctx, ctypes.c_void_p(out.data_ptr()), 1))
+        else:
+            self.render_batch(cameras, device_ptr=out.data_ptr())
+        return out
+
     def render_accum_relay(self, in_ptr: Optional[int], out_ptr: int) -> None:
         """Sort-last relay: continue the device image ``in_ptr`` (fragment colours of the bricks in front;
         ``None`` for the first brick) through this renderer's brick into ``out_ptr`` (may be the same)."""

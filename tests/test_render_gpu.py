@@ -320,3 +320,60 @@ def test_c2_vti_volumes_high_quality_camera_linked_light(tmp_path, golden_dir, n
     got, stats = _render_gpu(vol, cam, light, cfg, lut, size, size)
     assert stats["rays_hit"] > 300000 and got.any()
     assert_parity(got[rows[0]::rows[2]], want[rows[0]::rows[2]])
+
+
+def test_c3_full_size_view_matches_oracle():
+    """The headline configuration at BASELINE.json's full size: 512^3 double_sphere + normals, bounds +-1,
+    1920x1080, high_quality, turntable view 37, viridis + linear(0, 0.1).  One whole frame against the oracle
+    (about 2 s of CPU on the GPU box), plus the texture-unit alternative, plus size-independent properties:
+    empty-space skipping and the z-pair layout leave the float accumulators untouched."""
+    size, w, h = 512, 1920, 1080
+    data = create_sample_volume(size, "double_sphere")
+    normals = compute_normal_volume(data)                       # K2
+    vol = Volume(data=data, normals=normals, min_bounds=np.array([-1, -1, -1], np.float32),
+                 max_bounds=np.array([1, 1, 1], np.float32))
+    light, cfg, lut = Light.directional([1, -1, 0]), RenderConfig.high_quality(), viridis_lut(0.0, 0.1)
+    cam = turntable_camera(37)
+    want, _, counters = oracle.render(vol, cam, light, cfg, lut, w, h)
+    assert counters["samples"] > 3.0e8
+    accs = {}
+    for name, kw in (("default", {}), ("dense", dict(empty_space_skipping=False)), ("hwtex", dict(hardware_filtering=True)),
+                     ("f16", dict(texel_format="f16"))):
+        with VolumeRenderer(w, h, config=cfg, light=light, **kw) as r:
+            r.load_volume(vol)
+            r.set_camera(cam)
+            r.set_lut(lut)
+            got = np.frombuffer(r.render(), dtype=np.uint8).reshape(h, w, 4)
+            m = assert_parity(got, want)
+            assert abs(r.stats["samples"] - counters["samples"]) <= 1e-5 * counters["samples"], (name, r.stats, counters)
+            print(name, m, r.stats["samples_fetched"] / r.stats["samples"])
+            if name in ("default", "dense"):
+                accs[name] = r.render_accum()
+    assert np.array_equal(accs["default"], accs["dense"])
+    os.environ["PYVR_CUDA_PAIR"] = "0"
+    try:
+        with VolumeRenderer(w, h, config=cfg, light=light) as r:
+            r.load_volume(vol)
+            r.set_camera(cam)
+            r.set_lut(lut)
+            assert np.array_equal(r.render_accum(), accs["default"])
+    finally:
+        del os.environ["PYVR_CUDA_PAIR"]
+
+
+def test_render_tensor_is_the_same_frame_on_the_device(c1):
+    import torch
+
+    vol, light, lut = c1
+    cams = [turntable_camera(k) for k in (0, 90, 200)]
+    with VolumeRenderer(320, 200, config=RenderConfig.fast(), light=light) as r:
+        r.load_volume(vol)
+        r.set_lut(lut)
+        r.set_camera(cams[1])
+        host = np.frombuffer(r.render(), np.uint8).reshape(200, 320, 4)
+        dev = r.render_tensor()
+        assert dev.is_cuda and dev.dtype == torch.uint8 and np.array_equal(dev.cpu().numpy(), host)
+        batch = r.render_tensor(cams)
+        assert batch.shape == (3, 200, 320, 4) and np.array_equal(batch[1].cpu().numpy(), host)
+        with pytest.raises(ValueError):
+            r.render_tensor(out=torch.empty((1, 2, 3), dtype=torch.uint8, device="cuda"))
