@@ -220,6 +220,8 @@ __device__ __forceinline__ void index_slab(float X0, float D, float lo, float hi
     }
 }
 
+constexpr int MAX_IV = 6;   // active-interval table entries per ray (shared memory); refilled when exhausted
+
 #ifndef PYVR_MARCH_MIN_BLOCKS
 #define PYVR_MARCH_MIN_BLOCKS 7   // 7 CTAs x 4 warps per SM <=> at most 72 registers per thread
 #endif
@@ -415,52 +417,100 @@ march_kernel(const __grid_constant__ MarchArgs a) {
             acc.r = in.x; acc.g = in.y; acc.b = in.z; acc.a = in.w;
             if (acc.a >= a.term_alpha) { alive = false; last = i_lo - 1; }
         }
-        // ---- fast march, warp-synchronous.  Every round has two phases:
-        //   1. each live lane advances to its next sample that lies in an active macrocell (per-lane
-        //      loop over the cell map; lanes still inside a known active run pass straight through);
-        //   2. after a warp vote -- which also reconverges the lanes -- all lanes that have a sample
-        //      fetch and shade it together.
-        // The vote matters: without it the compiler lets the lanes that came out of the cell lookup and
-        // the lanes that skipped it run phase 2 as two separate half-empty groups (measured: 17 of 32
-        // lanes active in the gather).
+        // ---- fast march.  The ray first WALKS the cell map from j_lo to j_hi (cubes of like cells, see
+        // volume_pack.cu) and records the index intervals that lie in active cells -- adjacent active cubes
+        // merge, so a compact object is one interval -- in a small per-thread table in shared memory.  All 32
+        // lanes walk at once, each its own ray; doing the lookups inside the sampling loop instead made every
+        // round wait for the few lanes (8 of 32 on C3) that had just run off their cube.  The sampling loop is
+        // then warp-synchronous: a vote separates "advance to the next interval" from "gather + shade" and
+        // reconverges the warp (without it the compiler ran the gather as two half-empty groups).
         const bool ess = (a.flags & PYVR_FLAG_ESS) && vol.cell_dist != nullptr;
         const float hx = (float)vol.gn[0] - 0.5f, hy = (float)vol.gn[1] - 0.5f, hz = (float)vol.gn[2] - 0.5f;
-        // Per-ray constants of the cell walk.  Along an axis the ray leaves a cube of cells [c - r, c + r]
-        // through the face at voxel 8*(c + r + 1) (moving up) or 8*(c - r) (moving down):
-        //   face = 8*c + r*fstep + fbase,  fstep = +-8,  fbase = 8 or 0 (plus the brick origin);
-        // a zero direction component is treated as "up" with an infinite reciprocal, i.e. it never exits.
-        const float rDX = DX != 0.0f ? 1.0f / DX : 3.0e38f, rDY = DY != 0.0f ? 1.0f / DY : 3.0e38f,
-                    rDZ = DZ != 0.0f ? 1.0f / DZ : 3.0e38f;
         const int ogx = BRICK ? vol.org[0] : 0, ogy = BRICK ? vol.org[1] : 0, ogz = BRICK ? vol.org[2] : 0;
-        const int fstep_x = DX < 0.0f ? -8 : 8, fstep_y = DY < 0.0f ? -8 : 8, fstep_z = DZ < 0.0f ? -8 : 8;
-        const int fbase_x = (DX < 0.0f ? 0 : 8) + ogx, fbase_y = (DY < 0.0f ? 0 : 8) + ogy, fbase_z = (DZ < 0.0f ? 0 : 8) + ogz;
         const int max_last = a.max_steps - 1;
-        int run_end = ess ? i : 0x7fffffff;   // first index not known to lie in an active run of cells
+        __shared__ int s_iv[2 * MAX_IV][CTA_THREADS];   // [2k] = first index, [2k+1] = last index of interval k
+        int n_iv = 0, iv_next = 0;
+        int walk_i = i;            // where the walk resumes when the table has been consumed
+        bool walked = true;        // the walk has reached j_hi
+
+        // Walk from walk_i and (re)fill the table.
+        auto fill_table = [&]() {
+            // Per-ray constants of the walk.  Along an axis the ray leaves a cube of cells [c - r, c + r]
+            // through the face at voxel 8*(c + r + 1) (moving up) or 8*(c - r) (moving down):
+            //   face = 8*c + r*fstep + fbase,  fstep = +-8,  fbase = 8 or 0 (plus the brick origin);
+            // a zero direction component counts as "up" with an infinite reciprocal, i.e. it never exits.
+            const float rDX = DX != 0.0f ? 1.0f / DX : 3.0e38f, rDY = DY != 0.0f ? 1.0f / DY : 3.0e38f,
+                        rDZ = DZ != 0.0f ? 1.0f / DZ : 3.0e38f;
+            const int fstep_x = DX < 0.0f ? -8 : 8, fstep_y = DY < 0.0f ? -8 : 8, fstep_z = DZ < 0.0f ? -8 : 8;
+            const int fbase_x = (DX < 0.0f ? 0 : 8) + ogx, fbase_y = (DY < 0.0f ? 0 : 8) + ogy, fbase_z = (DZ < 0.0f ? 0 : 8) + ogz;
+            n_iv = 0; iv_next = 0; walked = true;
+            int cs = -1, ce = -1;          // the interval being built
+            int k = walk_i;
+            while (k <= j_hi) {
+                // Cell byte: b < 128: inactive, every cell within chessboard radius b-1 is inactive too;
+                // b >= 128: active, every cell within radius b-128 is active.  Either way the ray may run to
+                // the faces of that cube of cells: whole steps that stay inside it (and inside the volume) on
+                // every axis, conservative by 0.01 step.
+                const float fk = (float)k;
+                const float x = fmaf(fk, DX, X0), y = fmaf(fk, DY, Y0), z = fmaf(fk, DZ, Z0);
+                const int lx = max(__float2int_rd(x), 0) - ogx, ly = max(__float2int_rd(y), 0) - ogy,
+                          lz = max(__float2int_rd(z), 0) - ogz;     // lower tap, local to the stored block
+                const int b = __ldg(vol.cell_dist + ((lx >> 3) * vol.ncell[1] + (ly >> 3)) * vol.ncell[2] + (lz >> 3));
+                const bool active = b >= 128;
+                const int r = (b & 127) - (active ? 0 : 1);
+                const float fx = fminf(fmaxf((float)((lx & ~7) + r * fstep_x + fbase_x), -0.5f), hx);
+                const float fy = fminf(fmaxf((float)((ly & ~7) + r * fstep_y + fbase_y), -0.5f), hy);
+                const float fz = fminf(fmaxf((float)((lz & ~7) + r * fstep_z + fbase_z), -0.5f), hz);
+                const float tmin = fminf(fminf((fx - x) * rDX, (fy - y) * rDY), (fz - z) * rDZ);
+                const int stay = min(max(__float2int_rd(tmin - 0.01f), 1), 1 << 24);
+                if (active) {
+                    if (cs >= 0 && k > ce + 1) {         // a gap: close the interval being built
+                        if (n_iv == MAX_IV) { walked = false; break; }   // table full: resume here later
+                        s_iv[2 * n_iv][threadIdx.x] = cs; s_iv[2 * n_iv + 1][threadIdx.x] = ce; ++n_iv;
+                        cs = -1;
+                    }
+                    if (cs < 0) cs = k;
+                    ce = min(k + stay - 1, j_hi);
+                }
+                k += stay;
+            }
+            if (cs >= 0) {
+                if (walked && n_iv < MAX_IV) {
+                    s_iv[2 * n_iv][threadIdx.x] = cs; s_iv[2 * n_iv + 1][threadIdx.x] = ce; ++n_iv;
+                    k = j_hi + 1;
+                } else if (walked) {      // finished the walk with one interval too many
+                    walked = false; k = cs;
+                } else {
+                    k = cs;               // stopped at a gap: the open interval is re-walked on the refill
+                }
+            }
+            walk_i = k;
+        };
+
+        if (alive) {
+            if (ess) {
+                fill_table();
+            } else {                      // no skipping: one interval, the whole in-volume range
+                s_iv[0][threadIdx.x] = i; s_iv[1][threadIdx.x] = j_hi; n_iv = 1;
+            }
+        }
+        int run_end = i;                  // first index past the current interval
         while (true) {
             bool have = false;
             if (alive) {
-                while (i <= j_hi) {
-                    if (i < run_end) { have = true; break; }
-                    // Cell byte (volume_pack.cu): b < 128: inactive, every cell within chessboard radius
-                    // b-1 is inactive too; b >= 128: active, every cell within radius b-128 is active.
-                    // Either way the ray may run to the faces of that cube of cells: whole steps that stay
-                    // inside it (and inside the volume) on every axis, conservative by 0.01 step.
-                    const float fi = (float)i;
-                    const float x = fmaf(fi, DX, X0), y = fmaf(fi, DY, Y0), z = fmaf(fi, DZ, Z0);
-                    const int lx = max(__float2int_rd(x), 0) - ogx, ly = max(__float2int_rd(y), 0) - ogy,
-                              lz = max(__float2int_rd(z), 0) - ogz;     // lower tap, local to the stored block
-                    const int b = __ldg(vol.cell_dist + ((lx >> 3) * vol.ncell[1] + (ly >> 3)) * vol.ncell[2] + (lz >> 3));
-                    const bool active = b >= 128;
-                    const int r = (b & 127) - (active ? 0 : 1);
-                    const float fx = fminf(fmaxf((float)((lx & ~7) + r * fstep_x + fbase_x), -0.5f), hx);
-                    const float fy = fminf(fmaxf((float)((ly & ~7) + r * fstep_y + fbase_y), -0.5f), hy);
-                    const float fz = fminf(fmaxf((float)((lz & ~7) + r * fstep_z + fbase_z), -0.5f), hz);
-                    const float tmin = fminf(fminf((fx - x) * rDX, (fy - y) * rDY), (fz - z) * rDZ);
-                    const int stay = min(max(__float2int_rd(tmin - 0.01f), 1), 1 << 24);
-                    if (active) { run_end = i + stay; have = true; break; }
-                    i += stay;
+                if (i < run_end) {
+                    have = true;
+                } else {
+                    if (iv_next == n_iv && !walked) fill_table();      // rare: more than MAX_IV intervals
+                    if (iv_next < n_iv) {
+                        i = s_iv[2 * iv_next][threadIdx.x];
+                        run_end = s_iv[2 * iv_next + 1][threadIdx.x] + 1;
+                        ++iv_next;
+                        have = true;
+                    } else {
+                        alive = false;
+                    }
                 }
-                alive = have;
             }
             if (!__any_sync(0xffffffffu, have)) break;
             if (have) {
