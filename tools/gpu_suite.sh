@@ -31,12 +31,12 @@ done
 # ncu: launch list of a short default run, then one full capture of the march kernel
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/${TAG}_launches.csv \
     python bench.py --steps 2 --warmup 3 --views-per-step 12 --skip-cpu-baseline --no-alternatives > $OUT/${TAG}_ncu_launch.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:march_kernel -s 1 -c 1 -f -o $OUT/${TAG}_march \
+timeout 900 ncu --set full --clock-control none --import-source on -k "regex:^march_kernel" -s 1 -c 1 -f -o $OUT/${TAG}_march \
     python bench.py --steps 1 --warmup 1 --views-per-step 1 --skip-cpu-baseline > $OUT/${TAG}_ncu_full.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:march_kernel -s 1 -c 1 -f -o $OUT/${TAG}_march_noess \
+timeout 900 ncu --set full --clock-control none --import-source on -k "regex:^march_kernel" -s 1 -c 1 -f -o $OUT/${TAG}_march_noess \
     python bench.py --steps 1 --warmup 1 --views-per-step 1 --skip-cpu-baseline --no-ess > $OUT/${TAG}_ncu_full_noess.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:march_kernel -s 1 -c 1 -f -o $OUT/${TAG}_march_hwtex16 \
+timeout 900 ncu --set full --clock-control none --import-source on -k "regex:^march_kernel" -s 1 -c 1 -f -o $OUT/${TAG}_march_hwtex16 \
     python bench.py --steps 1 --warmup 1 --views-per-step 1 --skip-cpu-baseline --texels f16 --hwtex > $OUT/${TAG}_ncu_full_hwtex16.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:normals -c 1 -f -o $OUT/${TAG}_normals \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:normals_march -c 1 -f -o $OUT/${TAG}_normals \
     python bench.py --steps 1 --warmup 1 --views-per-step 1 --skip-cpu-baseline > $OUT/${TAG}_ncu_normals.log 2>&1
 ls -la $OUT | tail -30
