@@ -226,13 +226,16 @@ constexpr int MAX_IV = 6;   // active-interval table entries per ray (shared mem
 #define PYVR_MARCH_MIN_BLOCKS 7   // 7 CTAs x 4 warps per SM <=> at most 72 registers per thread
 #endif
 
+#ifndef PYVR_MARCH_MIN_BLOCKS_F16
+#define PYVR_MARCH_MIN_BLOCKS_F16 9   // f16x4 corners need half the registers: 56 per thread, 36 warps per SM (+5 %)
+#endif
 #ifndef PYVR_MARCH_MIN_BLOCKS_TEX
 #define PYVR_MARCH_MIN_BLOCKS_TEX 12   // the texture-unit variant holds no corner texels and is latency-bound: 40 registers,
                                        // 48 warps per SM (measured: 7 -> 699, 10 -> 890, 12 -> 939, 14 -> 583 Gsamples/s on C3)
 #endif
 
 template <bool STRICT, bool HALF, typename IDX, bool BRICK, bool PAIR, bool TEX>
-__global__ void __launch_bounds__(CTA_THREADS, TEX ? PYVR_MARCH_MIN_BLOCKS_TEX : PYVR_MARCH_MIN_BLOCKS)
+__global__ void __launch_bounds__(CTA_THREADS, TEX ? PYVR_MARCH_MIN_BLOCKS_TEX : (HALF && !STRICT) ? PYVR_MARCH_MIN_BLOCKS_F16 : PYVR_MARCH_MIN_BLOCKS)
 march_kernel(const __grid_constant__ MarchArgs a) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int px = blockIdx.x * TILE_W + (warp & 1) * WARP_W + (lane % WARP_W);
