@@ -137,6 +137,9 @@ class ClockSampler:
     def __enter__(self):
         self._thread = threading.Thread(target=self._run, daemon=True)
         self._thread.start()
+        t0 = time.perf_counter()
+        while not self.rows and time.perf_counter() - t0 < 0.5:     # first sample in hand before the timed region starts
+            time.sleep(0.001)
         return self
 
     def __exit__(self, *exc):
@@ -467,7 +470,7 @@ def main():
                 "l1": {"bound": "l1tex data stage", "achieved": achieved, "peak": l1_peak, "unit": "GB/s",
                        "frac": achieved / l1_peak,
                        "note": "same algorithmic bytes against 148 SMs x 128 B/clk at the sampled SM clock: the unit "
-                               "that actually binds this gather kernel (ncu: l1tex data-stage 61-75 % busy, issue slots 57-69 %, DRAM 14-24 %)"},
+                               "that actually binds this gather kernel (ncu: l1tex data-stage 71-76 % busy, issue slots 58-68 %, DRAM 16-24 %)"},
                 "algorithmic_bytes_per_sample": bytes_per_sample,
                 "samples_fetched_per_launch": fetched / max(launches, 1),
                 "samples_reference_per_launch": samples / max(launches, 1),
