@@ -24,12 +24,18 @@
 namespace pyvr {
 namespace {
 
-// Warp tile WARP_W x WARP_H pixels (one ray per lane), CTA = 2 x 2 warps.
+// Warp tile WARP_W x WARP_H pixels (one ray per lane), CTA = CTA_WX x CTA_WY warps.  Measured on C3: 8x4 warp
+// tiles in 2x2-warp CTAs (16x8 pixels, 128 threads) beat 1x2, 2x4, 4x2 and 4x4 warps per CTA by 2-29 %.
 #ifndef PYVR_WARP_W
 #define PYVR_WARP_W 8
 #endif
+#ifndef PYVR_CTA_WARPS_X
+#define PYVR_CTA_WARPS_X 2
+#define PYVR_CTA_WARPS_Y 2
+#endif
 constexpr int WARP_W = PYVR_WARP_W, WARP_H = 32 / WARP_W;
-constexpr int TILE_W = 2 * WARP_W, TILE_H = 2 * WARP_H, CTA_THREADS = TILE_W * TILE_H;
+constexpr int CTA_WX = PYVR_CTA_WARPS_X, CTA_WY = PYVR_CTA_WARPS_Y;
+constexpr int TILE_W = CTA_WX * WARP_W, TILE_H = CTA_WY * WARP_H, CTA_THREADS = TILE_W * TILE_H;
 
 struct Taps {
     int i0, i1;
@@ -238,8 +244,8 @@ template <bool STRICT, bool HALF, typename IDX, bool BRICK, bool PAIR, bool TEX>
 __global__ void __launch_bounds__(CTA_THREADS, TEX ? PYVR_MARCH_MIN_BLOCKS_TEX : (HALF && !STRICT) ? PYVR_MARCH_MIN_BLOCKS_F16 : PYVR_MARCH_MIN_BLOCKS)
 march_kernel(const __grid_constant__ MarchArgs a) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int px = blockIdx.x * TILE_W + (warp & 1) * WARP_W + (lane % WARP_W);
-    const int py = blockIdx.y * TILE_H + (warp >> 1) * WARP_H + (lane / WARP_W);
+    const int px = blockIdx.x * TILE_W + (warp % CTA_WX) * WARP_W + (lane % WARP_W);
+    const int py = blockIdx.y * TILE_H + (warp / CTA_WX) * WARP_H + (lane / WARP_W);
     const bool in_image = px < a.width && py < a.height;
 
     // image-space sharding: a CTA whose 64x64 tile group belongs to another rank only clears its pixels
