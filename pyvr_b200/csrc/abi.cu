@@ -763,12 +763,15 @@ int pyvr_cuda_render_batch(pyvr_ctx *c, const pyvr_view *views, int n, uint8_t *
         }
     } else {
         // ring of device slots: the march of group g overlaps the device->host copy of group g-1.  A group is
-        // up to kSlotViews views in one launch (fewer launch tails than one launch per view).
-        const int groups = (n + kSlotViews - 1) / kSlotViews;
-        rc = ensure_events(c, (size_t)groups);
+        // up to kSlotViews views in one launch (fewer launch tails than one launch per view); the groups taper
+        // towards the end (.., 4, 2, 1, 1) so that the copy left exposed after the last march is one frame.
+        rc = ensure_events(c, (size_t)n);
         if (rc != PYVR_OK) return rc;
-        for (int g = 0; g < groups; ++g) {
-            const int first = g * kSlotViews, m = n - first < kSlotViews ? n - first : kSlotViews;
+        int first = 0;
+        for (int g = 0; first < n; ++g) {
+            const int remaining = n - first;
+            int m = remaining / 2 < 1 ? 1 : remaining / 2;
+            if (m > kSlotViews) m = kSlotViews;
             const int slot = g % kRing;
             if (g >= kRing) CU(cudaStreamWaitEvent(c->stream, c->slot_copied[slot], 0));
             uchar4 *frames = c->frames + (size_t)slot * kSlotViews * frame_pixels(c);
@@ -778,6 +781,7 @@ int pyvr_cuda_render_batch(pyvr_ctx *c, const pyvr_view *views, int n, uint8_t *
             CU(cudaStreamWaitEvent(c->copy_stream, c->slot_rendered[slot], 0));
             CU(cudaMemcpyAsync(out + (size_t)first * frame_bytes, frames, frame_bytes * m, cudaMemcpyDeviceToHost, c->copy_stream));
             CU(cudaEventRecord(c->slot_copied[slot], c->copy_stream));
+            first += m;
         }
         CU(cudaStreamSynchronize(c->copy_stream));
     }
