@@ -154,6 +154,23 @@ __device__ __forceinline__ Corner8 gather(const VolumeDesc &v, const Taps &tx, c
     lerpf(lerpf(lerpf(k.c[0].field, k.c[1].field, wz), lerpf(k.c[2].field, k.c[3].field, wz), wy), \
           lerpf(lerpf(k.c[4].field, k.c[5].field, wz), lerpf(k.c[6].field, k.c[7].field, wz), wy), wx)
 
+__device__ __forceinline__ float rsqrt_approx(float x) {   // one MUFU.RSQ, no denormal fix-up sequence
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// LUT taps of the fast paths: same values as axis_taps, floor via F2I + I2FP instead of FRND + F2I.
+__device__ __forceinline__ Taps lut_taps(float u, int n) {
+    const float x = u * (float)n - 0.5f;
+    const int i = __float2int_rd(x);
+    Taps t;
+    t.f = x - (float)i;
+    t.i0 = min(max(i, 0), n - 1);
+    t.i1 = min(max(i + 1, 0), n - 1);
+    return t;
+}
+
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -170,7 +187,7 @@ __device__ __forceinline__ void shade(const MarchArgs &a, const float4 *s_lut, c
                                       float wx, float wy, float wz, Accum &acc) {
     const float density = PYVR_TRILERP(x);
     // texture(transfer_function_lut, vec2(density, 0.5)): linear, clamp-to-edge, row axis degenerate
-    const Taps tl = axis_taps(density, a.lut_size);
+    const Taps tl = STRICT ? axis_taps(density, a.lut_size) : lut_taps(density, a.lut_size);
     const float4 l0 = s_lut[tl.i0], l1 = s_lut[tl.i1];
     const float alpha_tf = lerpf(l0.w, l1.w, tl.f);
     if (!STRICT && alpha_tf == 0.0f) return;  // contributes exactly +0 to every accumulator
@@ -181,7 +198,7 @@ __device__ __forceinline__ void shade(const MarchArgs &a, const float4 *s_lut, c
     float nx = PYVR_TRILERP(y), ny = PYVR_TRILERP(z), nz = PYVR_TRILERP(w);
     float inv;
     if (STRICT) inv = 1.0f / sqrtf(nx * nx + ny * ny + nz * nz);
-    else inv = rsqrtf(fmaf(nz, nz, fmaf(ny, ny, nx * nx)));
+    else inv = rsqrt_approx(fmaf(nz, nz, fmaf(ny, ny, nx * nx)));
     nx *= inv; ny *= inv; nz *= inv;
     float ndotl;
     if (STRICT) ndotl = nx * a.ldir[0] + ny * a.ldir[1] + nz * a.ldir[2];
@@ -198,13 +215,13 @@ __device__ __forceinline__ void shade(const MarchArgs &a, const float4 *s_lut, c
 
 // Same for a texel the texture unit has already filtered (PYVR_FLAG_HWTEX), fast arithmetic.
 __device__ __forceinline__ void shade_filtered(const MarchArgs &a, const float4 *s_lut, const float4 &t, Accum &acc) {
-    const Taps tl = axis_taps(t.x, a.lut_size);
+    const Taps tl = lut_taps(t.x, a.lut_size);
     const float4 l0 = s_lut[tl.i0], l1 = s_lut[tl.i1];
     const float alpha_tf = lerpf(l0.w, l1.w, tl.f);
     if (alpha_tf == 0.0f) return;
     const float alpha = 1.0f - ex2_approx(alpha_tf * a.exp2_scale);
     const float cr = lerpf(l0.x, l1.x, tl.f), cg = lerpf(l0.y, l1.y, tl.f), cb = lerpf(l0.z, l1.z, tl.f);
-    const float inv = rsqrtf(fmaf(t.w, t.w, fmaf(t.z, t.z, t.y * t.y)));
+    const float inv = rsqrt_approx(fmaf(t.w, t.w, fmaf(t.z, t.z, t.y * t.y)));
     const float ndotl = fmaf(t.w * inv, a.ldir[2], fmaf(t.z * inv, a.ldir[1], t.y * inv * a.ldir[0]));
     const float light = fmaf(a.diffuse, fmaxf(ndotl, 0.0f), a.ambient);
     const float tr = 1.0f - acc.a;
