@@ -15,7 +15,7 @@ except Exception as e:
     print('$name FAILED', e); print(open('$OUT/${TAG}_$name.err').read()[-1500:])
 "; }
 run c3 --steps 6 --warmup 3
-run c4 --workload c4 --steps 4 --warmup 2
-[ "$WHICH" = all ] && run c5_p2p --workload c5 --exchange p2p --steps 4 --warmup 2
-[ "$WHICH" = all ] && run c5_nccl --workload c5 --exchange nccl --steps 4 --warmup 2
+run c4 --workload c4 --steps 20 --warmup 5
+[ "$WHICH" = all ] && run c5_p2p --workload c5 --exchange p2p --steps 20 --warmup 5
+[ "$WHICH" = all ] && run c5_nccl --workload c5 --exchange nccl --steps 20 --warmup 5
 true
