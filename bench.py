@@ -17,8 +17,8 @@ the views coming from pinned host memory and the RGBA8 frames read back to pinne
 the timed region.
 
 ``--impl reference`` times the CPU restatement of the reference shader (oracle/, C + OpenMP, all host
-threads) on a bounded row sample of the same views: the reference itself needs moderngl + an OpenGL
-driver, which do not exist in this image ("kind": "port").
+threads) on a bounded sample of the same workload -- the first few whole views of every step: the
+reference itself needs moderngl + an OpenGL driver, which do not exist in this image ("kind": "port").
 """
 
 from __future__ import annotations
@@ -202,21 +202,17 @@ def run_reference(args, rank):
     vol = Volume(data=data, normals=normals, min_bounds=np.array([-1, -1, -1], np.float32),
                  max_bounds=np.array([1, 1, 1], np.float32))
     per_step = args.views_per_step
-    # bounded sample: every `stride`-th row of each view of the step, sized for ~10 s per step
-    cam0 = turntable_camera(0)
-    cal_stride = max(args.height // 4, 1)
+    # bounded sample: the first `n_sample` WHOLE views of each step's 12 (whole views keep all host threads busy;
+    # a few rows per view would not), sized from one calibration view for about 3 s of CPU time per step
     t0 = time.perf_counter()
-    oracle.render(vol, cam0, light, config, lut, args.width, args.height, rows=(cal_stride // 2, args.height, cal_stride))
-    per_row = (time.perf_counter() - t0) / len(range(cal_stride // 2, args.height, cal_stride))
-    rows_per_view = max(1, int(10.0 / per_step / max(per_row, 1e-9)))
-    stride = max(args.height // min(rows_per_view, args.height), 1)
-    rows = range(stride // 2, args.height, stride)
+    oracle.render(vol, turntable_camera(0), light, config, lut, args.width, args.height)
+    t_view = time.perf_counter() - t0
+    n_sample = int(min(per_step, max(1, round(3.0 / max(t_view, 1e-6)))))
 
     def step(s):
         total = 0
-        for k in step_view_indices(s, 0, 1, per_step):
-            _, _, st = oracle.render(vol, turntable_camera(k), light, config, lut, args.width, args.height,
-                                     rows=(stride // 2, args.height, stride))
+        for k in step_view_indices(s, 0, 1, per_step)[:n_sample]:
+            _, _, st = oracle.render(vol, turntable_camera(k), light, config, lut, args.width, args.height)
             total += st["samples"]
         return total
 
@@ -226,14 +222,14 @@ def run_reference(args, rank):
     samples = sum(step(args.warmup + s) for s in range(args.steps))
     dt = time.perf_counter() - t0
     value = samples / dt / 1e9
-    sample = (f"every {stride}th row ({len(rows)} of {args.height}) of each of the {per_step} views per step; "
-              "CPU restatement of the reference shader (oracle/, C + OpenMP); the reference's ModernGL path "
-              "cannot run here (no moderngl, no OpenGL driver)")
+    sample = (f"the first {n_sample} whole views of each step's {per_step}; CPU restatement of the reference shader "
+              "(oracle/, C + OpenMP); the reference's ModernGL path cannot run here (no moderngl, no OpenGL driver)")
     line = {
         "impl": "reference", "metric": "ray-march throughput", "value": value, "unit": "Gsamples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "frames_per_s": args.steps * n_sample / dt,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, stride_note=f"rows subsampled 1/{stride}"),
+        "config": workload_config(args, stride_note=f"{n_sample} of {per_step} views per step"),
         "cpu_baseline": {"value": value, "unit": "Gsamples/s", "cores": oracle.num_threads(), "kind": "port",
                          "sample": sample},
         "e2e": {"value": value, "unit": "Gsamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
