@@ -11,14 +11,19 @@
 // transfer-function LUT is staged in shared memory once per CTA.
 //
 // Ray set-up (direction, slab test, entry point, validity of the entry sample) uses the oracle's
-// arithmetic in both modes.  After that there are two arithmetic modes (MarchArgs.flags):
+// arithmetic in every mode.  After that (MarchArgs.flags, template parameters):
 //   STRICT  statement-by-statement twin of the oracle: incremental position p += dir*step, IEEE
 //           divide / sqrt / expf, no skipping.  Used to pin the kernel against oracle/pyvr_oracle.c.
 //   fast    (default) the same sample lattice evaluated directly in voxel space,
 //           x(i) = X0 + i*DX (one FMA per axis): the in-volume index range [i_lo, i_hi] is found once
-//           per ray, clipped to the bounding box of the active macrocells, and marched with exact
-//           empty-space skipping over 8^3 macrocells; ex2.approx / rsqrt.approx.  Differences to
-//           STRICT are ~1e-6 relative.
+//           per ray and clipped to the bounding box of the active macrocells; the ray then walks the
+//           macrocell map once and records its active index intervals (exact empty-space skipping), and
+//           a warp-synchronous loop samples them; binary32 software trilinear, ex2.approx / rsqrt.approx.
+//           Differences to STRICT are ~1e-6 relative.
+//   TEX     the fast march with the gather + filter replaced by one tex3D fetch (PYVR_FLAG_HWTEX).
+//   BRICK   the fast march restricted to the samples a sort-last brick owns (pyvr_cuda_upload_brick);
+//   PAIR    z-pair entries: one LDG.256 / LDG.128 per corner row;  HALF  binary16 texels;
+//   in_acc  continue an incoming accumulation (relay);  shard_*  image-space tile sharding.
 #include "common.cuh"
 
 namespace pyvr {
