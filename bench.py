@@ -467,6 +467,10 @@ def main():
                        "frac": achieved / l1_peak,
                        "note": "same algorithmic bytes against 148 SMs x 128 B/clk at the sampled SM clock: the unit "
                                "that actually binds this gather kernel (ncu: l1tex data-stage 71-76 % busy, issue slots 58-68 %, DRAM 16-24 %)"},
+                "dram": ({"achieved": per_view * views_per_launch / (launch_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                          "frac": per_view * views_per_launch / (launch_ms * 1e-3) / 1e9 / peak,
+                          "note": "measured DRAM traffic per launch / kernel time: each packed line comes from HBM about "
+                                  "once per view, so HBM is far from binding"} if per_view else None),
                 "algorithmic_bytes_per_sample": bytes_per_sample,
                 "samples_fetched_per_launch": fetched / max(launches, 1),
                 "samples_reference_per_launch": samples / max(launches, 1),
