@@ -5,9 +5,9 @@ ctypes front end of ``oracle/liboracle.so`` (built from ``oracle/pyvr_oracle.c``
 ``bench.py``'s ``cpu_baseline`` / ``--impl reference`` leg.  Nothing under ``pyvr_b200/`` may
 import this package (``tests/test_no_oracle_in_product.py`` enforces it).
 
-PARITY STATUS: pixels are "parity unpinned" (no golden image upstream, no OpenGL here); see the
-header of ``pyvr_oracle.c``.  Normals, camera, LUT and sample-volume inputs are pinned by
-``tests/golden/``.
+PARITY STATUS: pinned.  ``oracle.gl`` runs the reference's shader files verbatim on Mesa llvmpipe (see its
+docstring) and ``tests/test_gl_reference.py`` holds this restatement to it (max |delta| = 1/255 on 19 scenes;
+``profiles/r02_gl_pin.json``).  Normals, camera, LUT and sample-volume inputs are pinned by ``tests/golden/``.
 
 The scene is assembled the way the reference renderer pushes its uniforms:
 bounds ``renderer.py:136-141``, matrices/camera position ``renderer.py:164-172``,
