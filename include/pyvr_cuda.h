@@ -215,6 +215,10 @@ int pyvr_cuda_stream_synchronize(int device, void *cuda_stream);
 /* Tuning knobs (no reference counterpart).  "swizzle": 1 (default) = L1 bank swizzle of the packed texel
  * layout, 0 = plain rows (for A/B profiling); must be set before pyvr_cuda_upload_volume. */
 int pyvr_cuda_set_option(pyvr_ctx *ctx, const char *key, int value);
+/* Roofline denominators measured on the spot (no reference counterpart; csrc/bandwidth.cu): bytes per second
+ * delivered to registers by coalesced 128-bit loads that hit L1 (level 1: the SM load-return path that bounds
+ * the march's texel gather) or stream from L2 with L1 bypassed (level 2).  *gbs in 1e9 bytes/s. */
+int pyvr_cuda_measure_cache_bandwidth(int device, int level, double *gbs);
 /* Page-locked host memory for frame read-back at full PCIe rate (cudaMallocHost / cudaFreeHost). */
 int pyvr_cuda_host_alloc(size_t bytes, void **out);
 int pyvr_cuda_host_free(void *ptr);

@@ -18,7 +18,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libpyvr_cuda.so")
-SOURCES = ["abi.cu", "march.cu", "volume_pack.cu", "normals.cu", "composite.cu", "synth.cu"]
+SOURCES = ["abi.cu", "march.cu", "volume_pack.cu", "normals.cu", "composite.cu", "synth.cu", "bandwidth.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
     "--shared", "-Xcompiler", "-fPIC,-ffp-contract=off", "-cudart", "static",
@@ -40,21 +40,29 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > built for d in deps)
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
-    """Compile the CUDA library if it is missing or older than its sources; returns its path."""
-    if not force and not needs_build():
+def build_library(force: bool = False, verbose: bool = False, defines=(), suffix: str = "") -> str:
+    """Compile the CUDA library if it is missing or older than its sources; returns its path.
+
+    ``defines`` / ``suffix`` build an experiment variant ``libpyvr_cuda_<suffix>.so`` with extra ``-D`` macros
+    (tools/gpu_ab.sh selects one with ``PYVR_CUDA_LIB``); the product is always the plain build."""
+    out = LIB_PATH if not suffix else os.path.join(PKG_DIR, f"libpyvr_cuda_{suffix}.so")
+    if not suffix and not force and not needs_build():
         return LIB_PATH
-    cmd = [_nvcc(), *NVCC_FLAGS, "-I", os.path.join(REPO, "include"), "-I", CSRC]
+    cmd = [_nvcc(), *NVCC_FLAGS, "-I", os.path.join(REPO, "include"), "-I", CSRC, *[f"-D{d}" for d in defines]]
     if verbose:
         cmd += ["-Xptxas", "-v"]
-    cmd += ["-o", LIB_PATH, *[os.path.join(CSRC, s) for s in SOURCES]]
+    cmd += ["-o", out, *[os.path.join(CSRC, s) for s in SOURCES]]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
     if verbose:
         print(proc.stderr)
-    return LIB_PATH
+    return out
 
 
 if __name__ == "__main__":
-    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    # python -m pyvr_b200._build [--force] [-v] [--variant NAME -DMACRO=1 ...]
+    argv = sys.argv[1:]
+    variant = argv[argv.index("--variant") + 1] if "--variant" in argv else ""
+    print(build_library(force="--force" in argv, verbose="-v" in argv,
+                        defines=[a[2:] for a in argv if a.startswith("-D")], suffix=variant))

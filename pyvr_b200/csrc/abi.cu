@@ -187,27 +187,29 @@ void fill_volume_desc(pyvr_ctx *c, const int local[3], const int global[3], cons
         v.voff[a] = (float)(-(double)bmin[a] * (double)v.gn[a] / ext - 0.5);
         v.ncell[a] = (v.n[a] + 7) / 8;
     }
-    // lines of SLOTS consecutive-z texels with an optional slot rotation; see common.cuh
+    // padded pitches (common.cuh): rows of n[2] + 2 entries, planes of n[1] + 2 rows, rounded up to the residue
+    // that rotates the L1 bank of texel (ix, iy, iz) by ix + 3*iy entries.  Measured best in round 1 among the
+    // linear maps tried, including the ones with the longest shortest collision vector (tools/swizzle_search.py),
+    // which were 10 % slower on the dense march: what matters is that the texels one quarter-warp touches -- a
+    // short run along the image-row direction -- spread over the banks.
     v.pair = c->use_pair ? 1 : 0;
-    v.slot_shift = (c->half_texels ? 4 : 3) - v.pair;
-    v.row_lines = (v.n[2] + (1 << v.slot_shift) - 1) >> v.slot_shift;
-    // slot = (iz + ix + 3*iy) mod SLOTS.  Measured best on C3 among the linear maps tried, including the ones
-    // with the longest shortest collision vector ((2,4,1) mod 8, (1,3,5) mod 16; tools/swizzle_search.py), which
-    // are 10 % slower on the dense march: what matters is that the texels one quarter-warp touches -- a short
-    // run along the image-row direction -- spread over the banks, not the distance between colliding texels.
-    v.swz_x = 0; v.swz_y = 0; v.swz_z = 1;
-    if (c->swizzle) {
-        v.swz_x = 1; v.swz_y = 3; v.swz_z = 1;
-        const char *env = getenv("PYVR_CUDA_SWZ");   // "x,y,z" override for experiments
-        int ex, ey, ez;
-        if (env && sscanf(env, "%d,%d,%d", &ex, &ey, &ez) == 3 && (ez & 1)) { v.swz_x = ex; v.swz_y = ey; v.swz_z = ez; }
+    const int slots = 128 / entry_bytes(c->half_texels, v.pair);
+    int rx = 1, ry = 3;
+    if (!c->swizzle) rx = ry = 0;
+    else {
+        const char *env = getenv("PYVR_CUDA_SWZ");   // "x,y" override for experiments
+        int ex, ey;
+        if (env && sscanf(env, "%d,%d", &ex, &ey) == 2) { rx = ex; ry = ey; }
     }
+    auto pad_to = [slots](long long len, int residue) {
+        const int r = ((residue % slots) + slots) % slots;
+        return len + (((r - len) % slots) + slots) % slots;
+    };
+    v.pitch_y = (int)pad_to(v.n[2] + 2, ry);
+    v.pitch_x = pad_to((long long)(v.n[1] + 2) * v.pitch_y, rx);
 }
 
-size_t texel_count(const pyvr_ctx *c) {
-    const VolumeDesc &v = c->vol;
-    return ((size_t)v.n[0] * v.n[1] * v.row_lines) << v.slot_shift;
-}
+size_t texel_count(const pyvr_ctx *c) { return (size_t)entry_count(c->vol); }
 
 int classify_cells(pyvr_ctx *c) {
     if (!c->have_volume || c->lut_size <= 0) return PYVR_OK;
@@ -300,6 +302,10 @@ int ensure_events(pyvr_ctx *c, size_t pairs) {
 MarchArgs make_args(const pyvr_ctx *c) {
     MarchArgs a{};
     a.vol = c->vol;
+    const long long eb = entry_bytes(c->half_texels, c->vol.pair);
+    a.tap_base = static_cast<const char *>(c->vol.texels) + texel_index(c->vol, 0, 0, 0) * eb;
+    a.stride_y = (long long)c->vol.pitch_y * eb;
+    a.stride_x = c->vol.pitch_x * eb;
     a.lut = c->lut;
     a.lut_size = c->lut_size;
     a.width = c->width;
@@ -482,7 +488,7 @@ int upload_packed(pyvr_ctx *c, const float *scalar, const float *normals, int sr
     CU(cudaMalloc(&c->cell_dist, c->n_cells));
     CU(cudaMalloc(&c->cell_scratch, c->n_cells));
     CU(cudaMalloc(&c->active_box, 6 * sizeof(int)));
-    if (n_tex != voxels) CU(cudaMemsetAsync(c->texels, 0, c->texel_bytes, c->stream));
+    CU(cudaMemsetAsync(c->texels, 0, c->texel_bytes, c->stream));   // row / plane padding is never read; keep it defined
     c->vol.texels = c->texels;
     c->vol.cell_dist = c->cell_dist;
     c->vol.active_box = c->active_box;
@@ -501,6 +507,7 @@ int upload_packed(pyvr_ctx *c, const float *scalar, const float *normals, int sr
         }
     }
     cudaError_t e = launch_pack_texels(d_scalar, d_normals, c->vol, c->half_texels, c->stream);
+    if (e == cudaSuccess) e = launch_fill_apron(c->vol, c->half_texels, c->stream);
     if (e == cudaSuccess) e = launch_cell_minmax(c->vol, c->half_texels, c->cell_minmax, c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     cudaFree(stage_s);
@@ -602,7 +609,7 @@ int pyvr_cuda_generate_volume(pyvr_ctx *c, int shape, int size, const int local_
     CU(cudaMalloc(&c->cell_dist, c->n_cells));
     CU(cudaMalloc(&c->cell_scratch, c->n_cells));
     CU(cudaMalloc(&c->active_box, 6 * sizeof(int)));
-    if (n_tex != (size_t)v.n[0] * v.n[1] * v.n[2]) CU(cudaMemsetAsync(c->texels, 0, c->texel_bytes, c->stream));
+    CU(cudaMemsetAsync(c->texels, 0, c->texel_bytes, c->stream));
     c->vol.texels = c->texels;
     c->vol.cell_dist = c->cell_dist;
     c->vol.active_box = c->active_box;
@@ -619,6 +626,7 @@ int pyvr_cuda_generate_volume(pyvr_ctx *c, int shape, int size, const int local_
     if (e == cudaSuccess) e = cudaEventCreate(&e1);
     if (e == cudaSuccess) e = cudaEventRecord(e0, c->stream);
     if (e == cudaSuccess) e = launch_synth_volume(c->vol, c->half_texels, shape, size, scratch, planes * plane, c->stream);
+    if (e == cudaSuccess) e = launch_fill_apron(c->vol, c->half_texels, c->stream);
     if (e == cudaSuccess) e = cudaEventRecord(e1, c->stream);
     if (e == cudaSuccess) e = launch_cell_minmax(c->vol, c->half_texels, c->cell_minmax, c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
@@ -661,8 +669,8 @@ int pyvr_cuda_set_pixel_shard(pyvr_ctx *c, int rank, int count) {
 int pyvr_cuda_set_lut(pyvr_ctx *c, const float *rgba, int size) {
     if (!c || !rgba) return fail(PYVR_ERR_INVALID, "NULL argument");
     if (size < 1) return fail(PYVR_ERR_INVALID, "LUT size must be at least 1, got %d", size);
-    if ((size_t)size * sizeof(float4) > 200 * 1024)
-        return fail(PYVR_ERR_INVALID, "LUT of %d entries does not fit in shared memory (max 12800)", size);
+    if (((size_t)size + 1) * 2 * sizeof(float4) > 200 * 1024)   // pair-packed in shared memory (march.cu, stage_lut)
+        return fail(PYVR_ERR_INVALID, "LUT of %d entries does not fit in shared memory (max 6399)", size);
     DeviceGuard guard(c->device);
     CU(cudaStreamSynchronize(c->stream));
     if (size != c->lut_size) {
@@ -891,6 +899,17 @@ int pyvr_cuda_compute_normals(int device, const float *in, float *out, int n0, i
     cudaFree(stage_in);
     cudaFree(stage_out);
     CU(e);
+    return PYVR_OK;
+}
+
+int pyvr_cuda_measure_cache_bandwidth(int device, int level, double *gbs) {
+    if (!gbs) return fail(PYVR_ERR_INVALID, "gbs is NULL");
+    if (level != 1 && level != 2) return fail(PYVR_ERR_INVALID, "level must be 1 (L1) or 2 (L2)");
+    int n_dev = 0;
+    CU(cudaGetDeviceCount(&n_dev));
+    if (device < 0 || device >= n_dev) return fail(PYVR_ERR_INVALID, "device %d out of range (%d visible)", device, n_dev);
+    DeviceGuard guard(device);
+    CU(measure_cache_bandwidth(level, gbs));
     return PYVR_OK;
 }
 

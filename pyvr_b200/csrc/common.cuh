@@ -13,19 +13,23 @@
 
 namespace pyvr {
 
-// Packed texel array.  Texels {s,nx,ny,nz} live in 128-byte lines of SLOTS = 128/texel_bytes
-// consecutive-z texels (8 for f32x4, 16 for f16x4); lines are ordered x-major, then y, then z:
-//   line(ix,iy,iz) = (ix*n[1] + iy) * row_lines + (iz >> slot_shift)
-//   slot(ix,iy,iz) = (swz_z*iz + swz_x*ix + swz_y*iy) & (SLOTS-1)
-//   texel index    = line * SLOTS + slot
-// The slot rotation ("swizzle") permutes texels inside their line.  One warp-wide corner load touches
-// a small planar patch of texels, typically many (x,y) rows at the same z; without the rotation they
-// all sit in the same slot of different lines, i.e. on the same L1 data banks, and the load
-// serialises into one data-stage wavefront per texel (measured: 18.6 wavefronts per LDG.128,
-// l1tex data pipe at 99 %).  With it they spread over the banks ("L1 bank swizzle").
+// Packed texel array.  Texels {s,nx,ny,nz} (float4, or 4 x binary16) are stored in plain [x][y][z] order with
+//   * a one-texel APRON on every side that replicates the edge texel (CLAMP_TO_EDGE made explicit): a sample's
+//     lower tap floor(x) ranges over [-1, n-1] and the upper tap is always lower + 1, so the fast march needs no
+//     index clamps and the four (x, y) corner rows of a sample sit at fixed distances from the first one;
+//   * PADDED PITCHES: one entry = one texel (or one z-pair, below); a row of entries along z is pitch_y entries
+//     long, an x-plane pitch_x entries, with pitch_y = 3 and pitch_x = 1 modulo S = 128 / entry_bytes.  One
+//     warp-wide corner load touches a small planar patch of texels, typically many (x, y) rows at the same z;
+//     with aligned rows they would all sit at the same offset of different 128-byte lines, i.e. on the same L1
+//     data banks, and the load would serialise (measured in round 1: 18.6 data-stage wavefronts per LDG.128, L1
+//     data pipe 99 % busy; 7.9 with the rotation).  The padding rotates the bank of texel (ix, iy, iz) by
+//     (ix + 3*iy) entries -- the round-1 slot swizzle -- without a single instruction in the march;
+//   * optional Z-PAIR entries (pair = 1): entry(ix, iy, iz) = {texel(iz), texel(iz + 1)} (2x memory): one 256-bit
+//     (f32x4) / 128-bit (f16x4) load fetches both z-taps of a corner row.
+//   entry index (ix, iy, iz) = (ix + 1) * pitch_x + (iy + 1) * pitch_y + (iz + 1),   ix in [-1, n[0]] etc.
 struct VolumeDesc {
-    const void *texels;   // float4 {s,nx,ny,nz} or 4 x half
-    int n[3];             // texel counts of the STORED array along world x, y, z.  NB world z is the
+    const void *texels;   // allocation start = entry (-1, -1, -1)
+    int n[3];             // texel counts of the STORED block along world x, y, z.  NB world z is the
                           // memory-fastest axis of the array the reference uploads: (nz, ny, nx) = numpy
                           // shape (0, 1, 2).
     // Sort-last bricks (pyvr_cuda_upload_brick): the stored array is the sub-block [org, org + n) of a
@@ -35,11 +39,9 @@ struct VolumeDesc {
     int gn[3], org[3];
     float own_lo[3], own_hi[3];
     int bricked;
-    int slot_shift;       // log2(entries per 128-byte line): 3 for f32x4, 4 for f16x4, one less with pairs
-    int pair;             // 1: every entry holds the z-pair {texel(iz), texel(min(iz+1, n-1))} (2x memory): one
-                          // 256-bit (f32x4) / 128-bit (f16x4) load fetches both z-taps of a trilinear corner row
-    int row_lines;        // lines per z-row = ceil(n[2] / SLOTS)
-    int swz_x, swz_y, swz_z;   // slot = (swz_z*iz + swz_x*ix + swz_y*iy) mod SLOTS; swz_z odd; (0, 0, 1) = no swizzle
+    int pair;             // 1: z-pair entries
+    int pitch_y;          // entries from (ix, iy, iz) to (ix, iy + 1, iz)
+    long long pitch_x;    // entries from (ix, iy, iz) to (ix + 1, iy, iz)
     float bmin[3], bmax[3];
     // fast path: voxel coordinate = world * vscale + voff  (= tc * n - 0.5)
     float vscale[3], voff[3];
@@ -53,14 +55,20 @@ struct VolumeDesc {
     int ncell[3];
 };
 
+// Entry index of texel (ix, iy, iz) of the stored block; -1 and n address the apron.
 __host__ __device__ __forceinline__ long long texel_index(const VolumeDesc &v, int ix, int iy, int iz) {
-    const long long line = ((long long)ix * v.n[1] + iy) * v.row_lines + (iz >> v.slot_shift);
-    const int slot = (v.swz_z * iz + v.swz_x * ix + v.swz_y * iy) & ((1 << v.slot_shift) - 1);
-    return (line << v.slot_shift) + slot;
+    return (long long)(ix + 1) * v.pitch_x + (long long)(iy + 1) * v.pitch_y + (iz + 1);
 }
+// entries of the whole allocation
+__host__ __device__ __forceinline__ long long entry_count(const VolumeDesc &v) { return (long long)(v.n[0] + 2) * v.pitch_x; }
 
 struct MarchArgs {
     VolumeDesc vol;
+    // fast path addressing: a sample with lower taps (ix, iy, iz) -- indices of the stored block, -1 = apron -- reads
+    // its four (x, y) corner rows at tap_base + entry_bytes * (ix*pitch_x + iy*pitch_y + iz) + {0, stride_y,
+    // stride_x, stride_x + stride_y}
+    const char *tap_base;          // address of entry (0, 0, 0)
+    long long stride_y, stride_x;  // pitch_y, pitch_x in bytes
     const pyvr_view *views;        // device array, indexed by blockIdx.z
     cudaTextureObject_t tex;       // PYVR_FLAG_HWTEX: the same texels as a 3-D array (width = z), linear filter, clamp
     const float4 *lut;             // device, lut_size entries
@@ -113,6 +121,8 @@ cudaError_t launch_finalize_rgba8(const float4 *accum, uchar4 *out, size_t n_pix
                                   cudaStream_t stream);
 cudaError_t launch_pack_texels(const float *scalar, const float *normals, const VolumeDesc &vol,
                                bool half_texels, cudaStream_t stream);
+// replicate the edge texels of the stored block into the one-texel apron (after every pack / generate)
+cudaError_t launch_fill_apron(const VolumeDesc &vol, bool half_texels, cudaStream_t stream);
 cudaError_t launch_cell_minmax(const VolumeDesc &vol, bool half_texels, float2 *cell_minmax,
                                cudaStream_t stream);
 constexpr int kCellDistCap = 15;      // distances saturate here (a nibble); a saturated value is a lower bound
@@ -128,5 +138,7 @@ cudaError_t launch_linearize_texels(const VolumeDesc &vol, bool half_texels, int
 cudaError_t launch_unpack_texels(const VolumeDesc &vol, bool half_texels, float *scalar, float *normals,
                                  cudaStream_t stream);
 cudaError_t launch_normals(const float *in, float *out, int n0, int n1, int n2, cudaStream_t stream);
+// bandwidth.cu: measured cache bandwidths (roofline denominators); level 1 = L1 load-return, 2 = L2 -> SM
+cudaError_t measure_cache_bandwidth(int level, double *gbs);
 
 }  // namespace pyvr

@@ -59,57 +59,82 @@ __device__ __forceinline__ Taps axis_taps(float u, int n) {
     return t;
 }
 
-// Same, from a voxel-space coordinate already known to lie in [-0.5, n-0.5].
-__device__ __forceinline__ Taps voxel_taps(float x, int n) {
-    const int i = __float2int_rd(x);   // F2I.FLOOR; the fraction comes from I2FP, not a second round-trip
-    Taps t;
-    t.f = x - (float)i;
-    t.i0 = max(i, 0);
-    t.i1 = min(i + 1, n - 1);
-    return t;
-}
-
-// z axis of the fast path.  Below the first texel centre (i = -1) both taps are texel 0 and the weight is
-// irrelevant; forcing it to 0 keeps that true for z-pair entries, whose second half is texel(i0 + 1).
-__device__ __forceinline__ Taps voxel_taps_z(float x, int n) {
-    const int i = __float2int_rd(x);
-    Taps t;
-    t.f = i < 0 ? 0.0f : x - (float)i;
-    t.i0 = max(i, 0);
-    t.i1 = min(i + 1, n - 1);
-    return t;
-}
-
 __device__ __forceinline__ float lerpf(float a, float b, float t) { return fmaf(t, b - a, a); }
 
-template <bool HALF, typename IDX>
-__device__ __forceinline__ float4 load_texel(const void *base, IDX idx) {
+// ---- packed binary32 pairs (sm_100: FADD2 / FMUL2 / FFMA2 work on 64-bit register pairs, one issue slot for two
+// IEEE operations).  A texel {s, nx, ny, nz} is two such pairs, so the trilinear filter of all four channels is
+// 14 packed lerps = 28 instructions instead of 56; every lane of a pair rounds exactly like the scalar fmaf().
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 lerp2(f32x2 a, f32x2 b, f32x2 t) {   // fma(t, b - a, a) per lane
+    f32x2 d, r;
+    asm("sub.f32x2 %0, %1, %2;" : "=l"(d) : "l"(b), "l"(a));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(t), "l"(d), "l"(a));
+    return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("mul.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
+struct Texel2 {
+    f32x2 sn, yz;   // {s, nx}, {ny, nz}
+};
+
+__device__ __forceinline__ f32x2 half2_to_f32x2(unsigned raw) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&raw));
+    return pack2(f.x, f.y);
+}
+
+// Both z-taps of one (x, y) corner row: entry(iz) and entry(iz + 1), or the two halves of one z-pair entry --
+// a single LDG.E.256 (f32x4 pairs, sm_100+) or LDG.E.128 (f16x4 pairs).
+template <bool HALF, bool PAIR>
+__device__ __forceinline__ void load_row(const char *p, Texel2 &lo, Texel2 &hi) {
     if constexpr (HALF) {
-        uint2 raw = __ldg(reinterpret_cast<const uint2 *>(base) + idx);
-        __half2 a = *reinterpret_cast<__half2 *>(&raw.x), b = *reinterpret_cast<__half2 *>(&raw.y);
-        float2 fa = __half22float2(a), fb = __half22float2(b);
-        return make_float4(fa.x, fa.y, fb.x, fb.y);
+        if constexpr (PAIR) {
+            const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(p));
+            lo.sn = half2_to_f32x2(raw.x); lo.yz = half2_to_f32x2(raw.y);
+            hi.sn = half2_to_f32x2(raw.z); hi.yz = half2_to_f32x2(raw.w);
+        } else {
+            const uint2 a = __ldg(reinterpret_cast<const uint2 *>(p)), b = __ldg(reinterpret_cast<const uint2 *>(p) + 1);
+            lo.sn = half2_to_f32x2(a.x); lo.yz = half2_to_f32x2(a.y);
+            hi.sn = half2_to_f32x2(b.x); hi.yz = half2_to_f32x2(b.y);
+        }
     } else {
-        return __ldg(reinterpret_cast<const float4 *>(base) + idx);
+        if constexpr (PAIR) {
+            asm("ld.global.nc.v4.b64 {%0, %1, %2, %3}, [%4];"
+                : "=l"(lo.sn), "=l"(lo.yz), "=l"(hi.sn), "=l"(hi.yz) : "l"(p));
+        } else {
+            asm("ld.global.nc.v2.b64 {%0, %1}, [%2];" : "=l"(lo.sn), "=l"(lo.yz) : "l"(p));
+            asm("ld.global.nc.v2.b64 {%0, %1}, [%2+16];" : "=l"(hi.sn), "=l"(hi.yz) : "l"(p));
+        }
     }
 }
 
-// One z-pair entry {texel(iz), texel(iz+1)}: a single LDG.E.128 (f16x4) or LDG.E.256 (f32x4, sm_100+).
-template <bool HALF, typename IDX>
-__device__ __forceinline__ void load_pair(const void *base, IDX idx, float4 &lo, float4 &hi) {
+// STRICT path: one texel by index (clamped taps, never the apron), unpacked.
+template <bool HALF>
+__device__ __forceinline__ float4 load_texel(const VolumeDesc &v, int ix, int iy, int iz) {
+    const long long e = texel_index(v, ix, iy, iz) << v.pair;    // first half of a z-pair entry = the texel itself
     if constexpr (HALF) {
-        const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(base) + idx);
-        const float2 a = __half22float2(*reinterpret_cast<const __half2 *>(&raw.x));
-        const float2 b = __half22float2(*reinterpret_cast<const __half2 *>(&raw.y));
-        const float2 c = __half22float2(*reinterpret_cast<const __half2 *>(&raw.z));
-        const float2 d = __half22float2(*reinterpret_cast<const __half2 *>(&raw.w));
-        lo = make_float4(a.x, a.y, b.x, b.y);
-        hi = make_float4(c.x, c.y, d.x, d.y);
+        const uint2 raw = __ldg(reinterpret_cast<const uint2 *>(v.texels) + e);
+        const float2 fa = __half22float2(*reinterpret_cast<const __half2 *>(&raw.x));
+        const float2 fb = __half22float2(*reinterpret_cast<const __half2 *>(&raw.y));
+        return make_float4(fa.x, fa.y, fb.x, fb.y);
     } else {
-        const char *p = reinterpret_cast<const char *>(base) + (size_t)idx * 32;
-        asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-            : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w), "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w)
-            : "l"(p));
+        return __ldg(reinterpret_cast<const float4 *>(v.texels) + e);
     }
 }
 
@@ -117,40 +142,13 @@ struct Corner8 {
     float4 c[8];  // index = (x_tap << 2) | (y_tap << 1) | z_tap
 };
 
-// Eight corner fetches from the line/slot layout of common.cuh.  IDX is int (packed array < 2^31
-// entries) or long long.  PAIR: four loads, each bringing both z-taps of one (x, y) row.
-template <bool HALF, typename IDX, bool BRICK, bool PAIR>
-__device__ __forceinline__ Corner8 gather(const VolumeDesc &v, const Taps &tx, const Taps &ty, const Taps &tz) {
-    constexpr int LS = (HALF ? 4 : 3) - (PAIR ? 1 : 0), SLOT_MASK = (1 << LS) - 1;
-    // taps are indices of the whole volume; a brick stores the sub-block that starts at v.org
-    const int x0 = BRICK ? tx.i0 - v.org[0] : tx.i0, x1 = BRICK ? tx.i1 - v.org[0] : tx.i1;
-    const int y0 = BRICK ? ty.i0 - v.org[1] : ty.i0, y1 = BRICK ? ty.i1 - v.org[1] : ty.i1;
-    const int z0 = BRICK ? tz.i0 - v.org[2] : tz.i0, z1 = BRICK ? tz.i1 - v.org[2] : tz.i1;
-    const IDX rx0 = (IDX)x0 * v.n[1], rx1 = (IDX)x1 * v.n[1];
-    const IDX l00 = (rx0 + y0) * v.row_lines, l01 = (rx0 + y1) * v.row_lines;
-    const IDX l10 = (rx1 + y0) * v.row_lines, l11 = (rx1 + y1) * v.row_lines;
-    const int lz0 = z0 >> LS, lz1 = z1 >> LS;
-    const int sx0 = v.swz_x * x0, sx1 = v.swz_x * x1, sy0 = v.swz_y * y0, sy1 = v.swz_y * y1;
-    const int s00 = sx0 + sy0, s01 = sx0 + sy1, s10 = sx1 + sy0, s11 = sx1 + sy1;
-#define PYVR_AT(l, s, lz, sz) ((((l) + (lz)) << LS) + (IDX)(((s) + (sz)) & SLOT_MASK))
-    const int q0 = v.swz_z * z0, q1 = v.swz_z * z1;
+template <bool HALF>
+__device__ __forceinline__ Corner8 gather_strict(const VolumeDesc &v, const Taps &tx, const Taps &ty, const Taps &tz) {
     Corner8 r;
-    if constexpr (PAIR) {
-        load_pair<HALF, IDX>(v.texels, PYVR_AT(l00, s00, lz0, q0), r.c[0], r.c[1]);
-        load_pair<HALF, IDX>(v.texels, PYVR_AT(l01, s01, lz0, q0), r.c[2], r.c[3]);
-        load_pair<HALF, IDX>(v.texels, PYVR_AT(l10, s10, lz0, q0), r.c[4], r.c[5]);
-        load_pair<HALF, IDX>(v.texels, PYVR_AT(l11, s11, lz0, q0), r.c[6], r.c[7]);
-    } else {
-        r.c[0] = load_texel<HALF, IDX>(v.texels, PYVR_AT(l00, s00, lz0, q0));
-        r.c[1] = load_texel<HALF, IDX>(v.texels, PYVR_AT(l00, s00, lz1, q1));
-        r.c[2] = load_texel<HALF, IDX>(v.texels, PYVR_AT(l01, s01, lz0, q0));
-        r.c[3] = load_texel<HALF, IDX>(v.texels, PYVR_AT(l01, s01, lz1, q1));
-        r.c[4] = load_texel<HALF, IDX>(v.texels, PYVR_AT(l10, s10, lz0, q0));
-        r.c[5] = load_texel<HALF, IDX>(v.texels, PYVR_AT(l10, s10, lz1, q1));
-        r.c[6] = load_texel<HALF, IDX>(v.texels, PYVR_AT(l11, s11, lz0, q0));
-        r.c[7] = load_texel<HALF, IDX>(v.texels, PYVR_AT(l11, s11, lz1, q1));
-    }
-#undef PYVR_AT
+    r.c[0] = load_texel<HALF>(v, tx.i0, ty.i0, tz.i0); r.c[1] = load_texel<HALF>(v, tx.i0, ty.i0, tz.i1);
+    r.c[2] = load_texel<HALF>(v, tx.i0, ty.i1, tz.i0); r.c[3] = load_texel<HALF>(v, tx.i0, ty.i1, tz.i1);
+    r.c[4] = load_texel<HALF>(v, tx.i1, ty.i0, tz.i0); r.c[5] = load_texel<HALF>(v, tx.i1, ty.i0, tz.i1);
+    r.c[6] = load_texel<HALF>(v, tx.i1, ty.i1, tz.i0); r.c[7] = load_texel<HALF>(v, tx.i1, ty.i1, tz.i1);
     return r;
 }
 
@@ -159,21 +157,10 @@ __device__ __forceinline__ Corner8 gather(const VolumeDesc &v, const Taps &tx, c
     lerpf(lerpf(lerpf(k.c[0].field, k.c[1].field, wz), lerpf(k.c[2].field, k.c[3].field, wz), wy), \
           lerpf(lerpf(k.c[4].field, k.c[5].field, wz), lerpf(k.c[6].field, k.c[7].field, wz), wy), wx)
 
-__device__ __forceinline__ float rsqrt_approx(float x) {   // one MUFU.RSQ, no denormal fix-up sequence
+__device__ __forceinline__ float rsqrt_approx(float x) {   // one MUFU.RSQ
     float y;
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
-}
-
-// LUT taps of the fast paths: same values as axis_taps, floor via F2I + I2FP instead of FRND + F2I.
-__device__ __forceinline__ Taps lut_taps(float u, int n) {
-    const float x = u * (float)n - 0.5f;
-    const int i = __float2int_rd(x);
-    Taps t;
-    t.f = x - (float)i;
-    t.i0 = min(max(i, 0), n - 1);
-    t.i1 = min(max(i + 1, 0), n - 1);
-    return t;
 }
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -186,31 +173,34 @@ struct Accum {
     float r, g, b, a;
 };
 
-// Shade + composite one sample (volume.frag.glsl:96-115).  `k` holds the 8 corner texels.
-template <bool STRICT>
-__device__ __forceinline__ void shade(const MarchArgs &a, const float4 *s_lut, const Corner8 &k,
-                                      float wx, float wy, float wz, Accum &acc) {
+// The transfer-function LUT in shared memory, pair-packed like the z-pair texels: entry j (0 <= j <= size) holds
+// {lut[max(j-1, 0)], lut[min(j, size-1)]}, i.e. both taps of a fetch whose lower tap floor(x) is j - 1.  A fetch is
+// one clamp of floor(x) to [-1, size-1] and two LDS.128 at one address; out-of-range densities land on an entry
+// whose halves are equal (CLAMP_TO_EDGE).
+__device__ __forceinline__ void stage_lut(float4 *s_lut, const float4 *lut, int size, int n_threads) {
+    for (int j = threadIdx.x; j <= size; j += n_threads) {
+        s_lut[2 * j] = lut[max(j - 1, 0)];
+        s_lut[2 * j + 1] = lut[min(j, size - 1)];
+    }
+}
+
+// Shade + composite one sample, STRICT arithmetic (volume.frag.glsl:96-115).  `k` holds the 8 corner texels.
+__device__ __forceinline__ void shade_strict(const MarchArgs &a, const float4 *s_lut, const Corner8 &k,
+                                             float wx, float wy, float wz, Accum &acc) {
     const float density = PYVR_TRILERP(x);
     // texture(transfer_function_lut, vec2(density, 0.5)): linear, clamp-to-edge, row axis degenerate
-    const Taps tl = STRICT ? axis_taps(density, a.lut_size) : lut_taps(density, a.lut_size);
-    const float4 l0 = s_lut[tl.i0], l1 = s_lut[tl.i1];
+    const Taps tl = axis_taps(density, a.lut_size);
+    const float4 l0 = s_lut[2 * (tl.i0 + 1)], l1 = s_lut[2 * (tl.i1 + 1)];
     const float alpha_tf = lerpf(l0.w, l1.w, tl.f);
-    if (!STRICT && alpha_tf == 0.0f) return;  // contributes exactly +0 to every accumulator
-    float alpha;
-    if (STRICT) alpha = 1.0f - expf(-alpha_tf * a.step / a.ref_step);
-    else alpha = 1.0f - ex2_approx(alpha_tf * a.exp2_scale);
+    const float alpha = 1.0f - expf(-alpha_tf * a.step / a.ref_step);
     const float cr = lerpf(l0.x, l1.x, tl.f), cg = lerpf(l0.y, l1.y, tl.f), cb = lerpf(l0.z, l1.z, tl.f);
     float nx = PYVR_TRILERP(y), ny = PYVR_TRILERP(z), nz = PYVR_TRILERP(w);
-    float inv;
-    if (STRICT) inv = 1.0f / sqrtf(nx * nx + ny * ny + nz * nz);
-    else inv = rsqrt_approx(fmaf(nz, nz, fmaf(ny, ny, nx * nx)));
+    const float inv = 1.0f / sqrtf(nx * nx + ny * ny + nz * nz);
     nx *= inv; ny *= inv; nz *= inv;
-    float ndotl;
-    if (STRICT) ndotl = nx * a.ldir[0] + ny * a.ldir[1] + nz * a.ldir[2];
-    else ndotl = fmaf(nz, a.ldir[2], fmaf(ny, a.ldir[1], nx * a.ldir[0]));
+    const float ndotl = nx * a.ldir[0] + ny * a.ldir[1] + nz * a.ldir[2];
     // fmaxf(NaN, 0) = 0: a zero-length normal gives the ambient term only (oracle header).
     const float diff = fmaxf(ndotl, 0.0f);
-    const float light = STRICT ? a.ambient + a.diffuse * diff : fmaf(a.diffuse, diff, a.ambient);
+    const float light = a.ambient + a.diffuse * diff;
     const float t = 1.0f - acc.a;
     acc.r = fmaf(t, cr * light * alpha, acc.r);
     acc.g = fmaf(t, cg * light * alpha, acc.g);
@@ -218,22 +208,32 @@ __device__ __forceinline__ void shade(const MarchArgs &a, const float4 *s_lut, c
     acc.a = fmaf(t, alpha, acc.a);
 }
 
-// Same for a texel the texture unit has already filtered (PYVR_FLAG_HWTEX), fast arithmetic.
-__device__ __forceinline__ void shade_filtered(const MarchArgs &a, const float4 *s_lut, const float4 &t, Accum &acc) {
-    const Taps tl = lut_taps(t.x, a.lut_size);
-    const float4 l0 = s_lut[tl.i0], l1 = s_lut[tl.i1];
-    const float alpha_tf = lerpf(l0.w, l1.w, tl.f);
+// LUT fetch + shading + front-to-back compositing of the fast paths.  density and the (not yet normalised)
+// normal are already filtered.  Returns without touching acc when alpha_tf == 0: such a sample contributes
+// exactly +0 to every accumulator.
+__device__ __forceinline__ void shade_fast(const MarchArgs &a, const float4 *s_lut, float density, float nx, float ny,
+                                           float nz, Accum &acc) {
+    const float x = density * (float)a.lut_size - 0.5f;     // the oracle's expression (cell_classify uses the same)
+    const int i = __float2int_rd(x);
+    const float f = x - (float)i;
+    const float4 *e = s_lut + 2 * (min(max(i, -1), a.lut_size - 1) + 1);
+    const float4 l0 = e[0], l1 = e[1];
+    const float alpha_tf = lerpf(l0.w, l1.w, f);
     if (alpha_tf == 0.0f) return;
     const float alpha = 1.0f - ex2_approx(alpha_tf * a.exp2_scale);
-    const float cr = lerpf(l0.x, l1.x, tl.f), cg = lerpf(l0.y, l1.y, tl.f), cb = lerpf(l0.z, l1.z, tl.f);
-    const float inv = rsqrt_approx(fmaf(t.w, t.w, fmaf(t.z, t.z, t.y * t.y)));
-    const float ndotl = fmaf(t.w * inv, a.ldir[2], fmaf(t.z * inv, a.ldir[1], t.y * inv * a.ldir[0]));
+    const f32x2 f2 = pack2(f, f);
+    float cr, cg;
+    unpack2(lerp2(pack2(l0.x, l0.y), pack2(l1.x, l1.y), f2), cr, cg);
+    const float cb = lerpf(l0.z, l1.z, f);
+    const float inv = rsqrt_approx(fmaf(nz, nz, fmaf(ny, ny, nx * nx)));
+    const float ndotl = fmaf(nz, a.ldir[2], fmaf(ny, a.ldir[1], nx * a.ldir[0])) * inv;
+    // fmaxf(NaN, 0) = 0: a zero-length normal (0 * inf) gives the ambient term only
     const float light = fmaf(a.diffuse, fmaxf(ndotl, 0.0f), a.ambient);
-    const float tr = 1.0f - acc.a;
-    acc.r = fmaf(tr, cr * light * alpha, acc.r);
-    acc.g = fmaf(tr, cg * light * alpha, acc.g);
-    acc.b = fmaf(tr, cb * light * alpha, acc.b);
-    acc.a = fmaf(tr, alpha, acc.a);
+    const float t = 1.0f - acc.a;
+    acc.r = fmaf(t, cr * light * alpha, acc.r);
+    acc.g = fmaf(t, cg * light * alpha, acc.g);
+    acc.b = fmaf(t, cb * light * alpha, acc.b);
+    acc.a = fmaf(t, alpha, acc.a);
 }
 
 // Index interval on which lo <= X0 + i*D <= hi, intersected into [enter, exit].
@@ -246,6 +246,20 @@ __device__ __forceinline__ void index_slab(float X0, float D, float lo, float hi
         enter = 3.0e38f;
         exit = -3.0e38f;
     }
+}
+
+#ifndef PYVR_PF_DIST
+#define PYVR_PF_DIST 0     // samples ahead to prefetch (0 = off); PYVR_PF_LEVEL 1 = L1, 2 = L2
+#endif
+#ifndef PYVR_PF_LEVEL
+#define PYVR_PF_LEVEL 2
+#endif
+__device__ __forceinline__ void prefetch_line(const char *p) {
+#if PYVR_PF_LEVEL == 1
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#endif
 }
 
 constexpr int MAX_IV = 6;   // active-interval table entries per ray (shared memory); refilled when exhausted
@@ -265,6 +279,7 @@ constexpr int MAX_IV = 6;   // active-interval table entries per ray (shared mem
 template <bool STRICT, bool HALF, typename IDX, bool BRICK, bool PAIR, bool TEX>
 __global__ void __launch_bounds__(CTA_THREADS, TEX ? PYVR_MARCH_MIN_BLOCKS_TEX : (HALF && !STRICT) ? PYVR_MARCH_MIN_BLOCKS_F16 : PYVR_MARCH_MIN_BLOCKS)
 march_kernel(const __grid_constant__ MarchArgs a) {
+    constexpr int ENTRY_BYTES = (HALF ? 8 : 16) << (PAIR ? 1 : 0);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int px = blockIdx.x * TILE_W + (warp % CTA_WX) * WARP_W + (lane % WARP_W);
     const int py = blockIdx.y * TILE_H + (warp / CTA_WX) * WARP_H + (lane / WARP_W);
@@ -286,7 +301,7 @@ march_kernel(const __grid_constant__ MarchArgs a) {
     }
 
     extern __shared__ float4 s_lut[];
-    for (int i = threadIdx.x; i < a.lut_size; i += CTA_THREADS) s_lut[i] = a.lut[i];
+    stage_lut(s_lut, a.lut, a.lut_size, CTA_THREADS);
     __syncthreads();
     const pyvr_view &vw = a.views[blockIdx.z];
     const VolumeDesc &vol = a.vol;
@@ -355,9 +370,8 @@ march_kernel(const __grid_constant__ MarchArgs a) {
                         ++n_samples; ++n_fetched;
                         const Taps tx = axis_taps(tcx, vol.gn[0]), ty = axis_taps(tcy, vol.gn[1]),
                                    tz = axis_taps(tcz, vol.gn[2]);
-                        // (z-pair entries: below the first texel centre both taps are texel 0, so the weight is moot)
-                        const Corner8 c8 = gather<HALF, IDX, false, PAIR>(vol, tx, ty, tz);
-                        shade<true>(a, s_lut, c8, tx.f, ty.f, PAIR && tz.i1 == tz.i0 && tz.i0 == 0 ? 0.0f : tz.f, acc);
+                        const Corner8 c8 = gather_strict<HALF>(vol, tx, ty, tz);
+                        shade_strict(a, s_lut, c8, tx.f, ty.f, tz.f, acc);
                     }
                     pxw += sx; pyw += sy; pzw += sz;
                 }
@@ -556,11 +570,38 @@ march_kernel(const __grid_constant__ MarchArgs a) {
                 if constexpr (TEX) {
                     // texel centres sit at integer + 0.5 in unnormalised texture space; width = z
                     const float4 t = tex3D<float4>(a.tex, z + 0.5f - (float)ogz, y + 0.5f - (float)ogy, x + 0.5f - (float)ogx);
-                    shade_filtered(a, s_lut, t, acc);
+                    shade_fast(a, s_lut, t.x, t.y, t.z, t.w, acc);
                 } else {
-                    const Taps tx = voxel_taps(x, vol.gn[0]), ty = voxel_taps(y, vol.gn[1]), tz = voxel_taps_z(z, vol.gn[2]);
-                    const Corner8 c8 = gather<HALF, IDX, BRICK, PAIR>(vol, tx, ty, tz);
-                    shade<false>(a, s_lut, c8, tx.f, ty.f, tz.f, acc);
+                    // lower taps floor(x) in [-1, n-1] (the apron holds the clamped texels), upper taps = lower + 1
+                    const int ix = __float2int_rd(x), iy = __float2int_rd(y), iz = __float2int_rd(z);
+                    const float wx = x - (float)ix, wy = y - (float)iy, wz = z - (float)iz;
+                    const IDX e = (IDX)(ix - ogx) * (IDX)vol.pitch_x + (IDX)(iy - ogy) * (IDX)vol.pitch_y + (IDX)(iz - ogz);
+                    const char *p00 = a.tap_base + (long long)e * ENTRY_BYTES;
+                    const char *p01 = p00 + a.stride_y, *p10 = p00 + a.stride_x, *p11 = p10 + a.stride_y;
+                    Texel2 c000, c001, c010, c011, c100, c101, c110, c111;
+                    load_row<HALF, PAIR>(p00, c000, c001);
+                    load_row<HALF, PAIR>(p01, c010, c011);
+                    load_row<HALF, PAIR>(p10, c100, c101);
+                    load_row<HALF, PAIR>(p11, c110, c111);
+#if PYVR_PF_DIST > 0
+                    if (i + PYVR_PF_DIST < run_end) {   // warm the lines of a later sample of this interval
+                        const float fp = fi + (float)PYVR_PF_DIST;
+                        const int jx = __float2int_rd(fmaf(fp, DX, X0)), jy = __float2int_rd(fmaf(fp, DY, Y0)),
+                                  jz = __float2int_rd(fmaf(fp, DZ, Z0));
+                        const IDX ep = (IDX)(jx - ogx) * (IDX)vol.pitch_x + (IDX)(jy - ogy) * (IDX)vol.pitch_y + (IDX)(jz - ogz);
+                        const char *q = a.tap_base + (long long)ep * ENTRY_BYTES;
+                        prefetch_line(q);
+                        prefetch_line(q + a.stride_x + a.stride_y);
+                    }
+#endif
+                    // filter order of the oracle: z (memory-fastest) first, then y, then x; {s, nx} and {ny, nz} packed
+                    const f32x2 tz2 = pack2(wz, wz), ty2 = pack2(wy, wy), tx2 = pack2(wx, wx);
+                    float density, nx, ny, nz;
+                    unpack2(lerp2(lerp2(lerp2(c000.sn, c001.sn, tz2), lerp2(c010.sn, c011.sn, tz2), ty2),
+                                  lerp2(lerp2(c100.sn, c101.sn, tz2), lerp2(c110.sn, c111.sn, tz2), ty2), tx2), density, nx);
+                    unpack2(lerp2(lerp2(lerp2(c000.yz, c001.yz, tz2), lerp2(c010.yz, c011.yz, tz2), ty2),
+                                  lerp2(lerp2(c100.yz, c101.yz, tz2), lerp2(c110.yz, c111.yz, tz2), ty2), tx2), ny, nz);
+                    shade_fast(a, s_lut, density, nx, ny, nz, acc);
                 }
                 if (acc.a >= a.term_alpha) {
                     terminated = i < max_last;
@@ -600,9 +641,17 @@ march_kernel(const __grid_constant__ MarchArgs a) {
 
 template <bool STRICT, bool HALF, typename IDX, bool BRICK, bool PAIR, bool TEX = false>
 cudaError_t launch_one(const MarchArgs &a, int n_views, cudaStream_t stream) {
-    const size_t smem = (size_t)a.lut_size * sizeof(float4);
+    const size_t smem = ((size_t)a.lut_size + 1) * 2 * sizeof(float4);   // pair-packed LUT (stage_lut)
     auto kern = march_kernel<STRICT, HALF, IDX, BRICK, PAIR, TEX>;
-    if (smem > 48 * 1024) {
+    // dynamic + static shared memory above the 48 KiB default needs the opt-in (static = the interval table)
+    static size_t static_smem = ~(size_t)0;
+    if (static_smem == ~(size_t)0) {
+        cudaFuncAttributes attr;
+        cudaError_t e = cudaFuncGetAttributes(&attr, kern);
+        if (e != cudaSuccess) return e;
+        static_smem = attr.sharedSizeBytes;
+    }
+    if (smem + static_smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }

@@ -51,6 +51,40 @@ pack_texels_kernel(const float *__restrict__ scalar, const float *__restrict__ n
     }
 }
 
+// Apron fill, one axis at a time (z, then y, then x), so that edges and corners end up replicated too.
+// AXIS 2: entries (ix, iy, -1) and (ix, iy, n2) for the interior (ix, iy); AXIS 1: (ix, -1 | n1, iz) for
+// interior ix and every iz in [-1, n2]; AXIS 0: (-1 | n0, iy, iz) for every iy, iz including their aprons.
+// A z-pair entry (ix, iy, iz) holds {T(cz(iz)), T(cz(iz + 1))} with cz = clamp to [0, n2 - 1]: copying the
+// entry of the clamped (ix, iy) at the SAME iz is right for axes 0 and 1; on axis 2 entry(-1) = {T(0), T(0)}
+// takes the first half of entry(0) twice and entry(n2) = entry(n2 - 1) = {T(n2-1), T(n2-1)}.
+template <typename ENTRY, int AXIS>
+__global__ void __launch_bounds__(256)
+fill_apron_kernel(VolumeDesc v) {
+    ENTRY *e = reinterpret_cast<ENTRY *>(const_cast<void *>(v.texels));
+    const int n0 = v.n[0], n1 = v.n[1], n2 = v.n[2];
+    const long long span_a = AXIS == 2 ? n0 : AXIS == 1 ? n0 : n1 + 2;
+    const long long span_b = AXIS == 2 ? n1 : n2 + 2;
+    const long long total = 2 * span_a * span_b;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const int side = (int)(t & 1);
+        const long long r = t >> 1;
+        const int b = (int)(r % span_b), a = (int)(r / span_b);
+        int ix, iy, iz, sx, sy, sz;
+        if (AXIS == 2) { ix = sx = a; iy = sy = b; iz = side ? n2 : -1; sz = side ? n2 - 1 : 0; }
+        else if (AXIS == 1) { ix = sx = a; iz = sz = b - 1; iy = side ? n1 : -1; sy = side ? n1 - 1 : 0; }
+        else { iy = sy = a - 1; iz = sz = b - 1; ix = side ? n0 : -1; sx = side ? n0 - 1 : 0; }
+        ENTRY val = e[texel_index(v, sx, sy, sz)];
+        if (AXIS == 2 && !side && v.pair) {   // {T(0), T(0)}
+            if constexpr (sizeof(ENTRY) == 32) { val.hi = val.lo; }
+            else if constexpr (sizeof(ENTRY) == 16) { val.z = val.x; val.w = val.y; }
+        }
+        e[texel_index(v, ix, iy, iz)] = val;
+    }
+}
+
+struct Entry32 { float4 lo, hi; };   // f32x4 z-pair
+
 // scalar of entry idx (the first texel of a z-pair entry)
 template <bool HALF>
 __device__ __forceinline__ float load_scalar(const void *base, long long idx, int pair) {
@@ -204,6 +238,26 @@ cudaError_t launch_pack_texels(const float *scalar, const float *normals, const 
     if (half_texels) pack_texels_kernel<true><<<grid, 256, 0, stream>>>(scalar, normals, vol);
     else pack_texels_kernel<false><<<grid, 256, 0, stream>>>(scalar, normals, vol);
     return cudaGetLastError();
+}
+
+template <typename ENTRY>
+static cudaError_t fill_apron_all(const VolumeDesc &vol, cudaStream_t stream) {
+    const long long wz = 2LL * vol.n[0] * vol.n[1], wy = 2LL * vol.n[0] * (vol.n[2] + 2),
+                    wx = 2LL * (vol.n[1] + 2) * (vol.n[2] + 2);
+    fill_apron_kernel<ENTRY, 2><<<grid_for(wz, 256), 256, 0, stream>>>(vol);
+    fill_apron_kernel<ENTRY, 1><<<grid_for(wy, 256), 256, 0, stream>>>(vol);
+    fill_apron_kernel<ENTRY, 0><<<grid_for(wx, 256), 256, 0, stream>>>(vol);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fill_apron(const VolumeDesc &vol, bool half_texels, cudaStream_t stream) {
+    // entry sizes: f16x4 8 B (uint2), f16x4 pair / f32x4 16 B (uint4), f32x4 pair 32 B
+    if (half_texels && !vol.pair) {
+        // 8-byte entries: reuse the 16-byte kernel's logic through a dedicated instantiation
+        return fill_apron_all<uint2>(vol, stream);
+    }
+    if (half_texels || !vol.pair) return fill_apron_all<uint4>(vol, stream);
+    return fill_apron_all<Entry32>(vol, stream);
 }
 
 cudaError_t launch_cell_minmax(const VolumeDesc &vol, bool half_texels, float2 *cell_minmax,

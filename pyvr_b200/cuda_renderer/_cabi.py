@@ -85,6 +85,7 @@ SYMBOLS = {
     "pyvr_cuda_memcpy": (_i, [_i, _vp, _vp, _c.c_size_t, _i, _vp]),
     "pyvr_cuda_stream_synchronize": (_i, [_i, _vp]),
     "pyvr_cuda_set_option": (_i, [_vp, _c.c_char_p, _i]),
+    "pyvr_cuda_measure_cache_bandwidth": (_i, [_i, _i, _c.POINTER(_c.c_double)]),
     "pyvr_cuda_host_alloc": (_i, [_c.c_size_t, _c.POINTER(_vp)]),
     "pyvr_cuda_host_free": (_i, [_vp]),
     "pyvr_cuda_device_count": (_i, [_c.POINTER(_i)]),
@@ -129,6 +130,13 @@ def device_count() -> int:
     n = _c.c_int(0)
     check(lib().pyvr_cuda_device_count(_c.byref(n)))
     return n.value
+
+
+def measure_cache_bandwidth(level: int, device: int = 0) -> float:
+    """GB/s delivered to registers by coalesced 128-bit loads served from L1 (``level=1``) or L2 (``level=2``)."""
+    gbs = _c.c_double(0.0)
+    check(lib().pyvr_cuda_measure_cache_bandwidth(int(device), int(level), _c.byref(gbs)))
+    return gbs.value
 
 
 def f32_ptr(a: np.ndarray):
