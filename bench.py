@@ -8,17 +8,24 @@ Workload (SURVEY.md section 8 d, C3 = BASELINE.json configs[2]): synthetic 512^3
 (step 0.005, 1000 steps, reference step 0.01), ``Light.directional([1,-1,0])``, viridis colour TF +
 ``linear(0, 0.1)`` opacity TF, the 360-view turntable (azimuth 2*pi*k/360, elevation pi/6, distance 3).
 
-A *step* is one batch of ``--views-per-step`` turntable views per GPU.  Views are dealt ``k mod N``
-over the N ranks (no data-path collective; every rank holds the whole volume), so per-GPU work is
-fixed as N grows: ``"scaling": "weak"``.  A *sample* is one in-box loop body of the reference shader
-(volume.frag.glsl:92-116), counted by the kernel; ``value`` = samples of all ranks / max-over-ranks
-device time, frames device-resident.  ``e2e`` = the same through ``VolumeRenderer.render_batch`` with
-the views coming from pinned host memory and the RGBA8 frames read back to pinned host memory inside
-the timed region.
+A *step* is one batch of ``--views-per-step`` turntable views per GPU (default 180 = half a revolution, so
+that the driver's 20 timed steps last about two seconds).  Views are dealt ``k mod N`` over the N ranks (no
+data-path collective; every rank holds the whole volume), so per-GPU work is fixed as N grows:
+``"scaling": "weak"``.  A *sample* is one in-box loop body of the reference shader (volume.frag.glsl:92-116),
+counted by the kernel; ``value`` = samples of all ranks / max-over-ranks device time, frames
+device-resident.  ``e2e`` = the same through ``VolumeRenderer.render_batch`` with the views coming from
+pinned host memory and the RGBA8 frames read back to pinned host memory inside the timed region.
 
-``--impl reference`` times the CPU restatement of the reference shader (oracle/, C + OpenMP, all host
-threads) on a bounded sample of the same workload -- the first few whole views of every step: the
-reference itself needs moderngl + an OpenGL driver, which do not exist in this image ("kind": "port").
+``--impl reference`` times the reference's own shader (pyvr/shaders/volume.frag.glsl, verbatim) on Mesa
+llvmpipe on the host cores -- the baseline BASELINE.json names -- through ``oracle/gl`` (a ctypes replay of
+pyvr/moderngl_renderer/manager.py; moderngl itself is not in the image): ``"kind": "reference"``.  One step =
+one whole 1920x1080 view of the same turntable (a bounded sample of the GPU arm's step).  If the Mesa
+library is missing it falls back to the C/OpenMP restatement (``oracle/``, ``"kind": "port"``).
+
+At N > 1 the line also carries ``secondary`` (time-boxed C4 image-tile and C5 sort-last lines, see
+bench_partitioned.py) and ``parity_check`` (tile-sharded frame == single-GPU frame bit for bit, bricked
+composite vs single GPU within tolerance, relay bit-identical), so that the multi-process paths are
+measured and checked under the driver.
 """
 
 from __future__ import annotations
@@ -44,7 +51,7 @@ BYTES_PER_SAMPLE_F16 = 64
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3", choices=["c3", "c4", "c5"],
@@ -54,14 +61,18 @@ def parse_args():
     ap.add_argument("--width", type=int, default=None)
     ap.add_argument("--height", type=int, default=None)
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="c5: binary-swap exchange path")
-    ap.add_argument("--views-per-step", type=int, default=12)
+    ap.add_argument("--views-per-step", type=int, default=180)
     ap.add_argument("--texels", default="f32", choices=["f32", "f16"])
     ap.add_argument("--no-ess", action="store_true", help="disable empty-space skipping")
     ap.add_argument("--hwtex", action="store_true", help="sample through the texture unit (hardware trilinear)")
     ap.add_argument("--layout", default=None, choices=["linear", "swizzle"])
-    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
-    ap.add_argument("--no-alternatives", action="store_true", help="skip the f16 / hwtex side measurements")
+    ap.add_argument("--no-alternatives", action="store_true", help="skip the f16 / hwtex / dense side measurements")
+    ap.add_argument("--no-secondary", action="store_true", help="N > 1: skip the C4 / C5 lines and the parity check")
+    ap.add_argument("--secondary-seconds", type=float, default=240.0, help="N > 1: time box of the secondary section")
+    ap.add_argument("--reference-backend", default="auto", choices=["auto", "gl", "oracle"],
+                    help="CPU arm: gl = the reference's GLSL on Mesa llvmpipe; oracle = C/OpenMP restatement")
     return ap.parse_args()
 
 
@@ -165,27 +176,94 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def cpu_baseline(data, normals, light, config, lut, args, view_indices, target_seconds):
-    """Oracle (C + OpenMP restatement of the reference shader) on a bounded sample of the same workload: whole
-    views of the step, one after the other, until `target_seconds` of CPU time have been spent."""
-    import oracle
-    from pyvr_b200 import Volume
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
 
-    vol = Volume(data=data, normals=normals, min_bounds=np.array([-1, -1, -1], np.float32),
-                 max_bounds=np.array([1, 1, 1], np.float32))
-    samples, views, t0 = 0, 0, time.perf_counter()
+
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm is meant to use every host core.  Must run
+    before the OpenMP runtime of liboracle.so initialises and before llvmpipe creates its rasteriser threads."""
+    n = host_threads()
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    os.environ["LP_NUM_THREADS"] = str(min(n, 16))     # Mesa 18 caps llvmpipe at 16 rasteriser threads
+    return n
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU arm: the reference's shader on Mesa llvmpipe (oracle/gl), else the C/OpenMP restatement (oracle/)
+# --------------------------------------------------------------------------------------------------
+class CpuReference:
+    """C3 scene loaded once into the CPU renderer; ``render_view(k)`` = one whole 1920x1080 turntable view."""
+
+    def __init__(self, args, data, normals, light, config, lut, backend="auto"):
+        import oracle
+        from pyvr_b200 import Volume
+
+        self.args, self.light, self.config, self.lut = args, light, config, lut
+        self.vol = Volume(data=data, normals=normals, min_bounds=np.array([-1, -1, -1], np.float32),
+                          max_bounds=np.array([1, 1, 1], np.float32))
+        self.oracle, self.gl, self.kind = oracle, None, "port"
+        self.cores = oracle.num_threads()
+        self.what = ("CPU restatement of the reference shader (oracle/pyvr_oracle.c, C + OpenMP); Mesa llvmpipe "
+                     "not available on this box")
+        if backend in ("auto", "gl"):
+            try:
+                import oracle.gl as ogl
+
+                r = ogl.GLReference(args.width, args.height)
+                r.load_shaders()
+                r.set_config(config.step_size, config.max_steps, config.reference_step_size)
+                r.set_light(light.ambient_intensity, light.diffuse_intensity, light.position, light.target)
+                r.load_volume(self.vol.data, self.vol.normals, self.vol.min_bounds, self.vol.max_bounds)
+                r.set_lut(lut)
+                self.gl, self.kind = r, "reference"
+                self.cores = int(os.environ.get("LP_NUM_THREADS", min(host_threads(), 16)))
+                self.what = ("the reference's own GLSL (pyvr/shaders/volume.frag.glsl, verbatim) on " + r.info["renderer"]
+                             + ", " + r.info["version"] + ", driven as pyvr/moderngl_renderer/manager.py drives it "
+                             "(oracle/gl: ctypes OpenGL, moderngl is not in the image); clear + draw + glReadPixels per view")
+            except Exception as e:   # GLUnavailable, compile errors, ...
+                if backend == "gl":
+                    raise
+                self.what += f" ({type(e).__name__}: {e})"
+
+    def samples_of(self, k):
+        """Reference samples of view k (the unit of the metric): counted by the restatement, which executes the
+        same loop bodies as the shader (tests/test_gl_reference.py)."""
+        _, _, st = self.oracle.render(self.vol, turntable_camera(k), self.light, self.config, self.lut,
+                                      self.args.width, self.args.height)
+        return st["samples"]
+
+    def render_view(self, k):
+        """Returns (seconds, samples or None).  With GL the sample count comes from ``samples_of`` (untimed)."""
+        cam = turntable_camera(k)
+        t0 = time.perf_counter()
+        if self.gl is not None:
+            pos, _ = cam.get_camera_vectors()
+            self.gl.set_camera(cam.get_view_matrix(), cam.get_projection_matrix(self.args.width / self.args.height), pos)
+            self.gl.render()
+            return time.perf_counter() - t0, None
+        _, _, st = self.oracle.render(self.vol, cam, self.light, self.config, self.lut, self.args.width, self.args.height)
+        return time.perf_counter() - t0, st["samples"]
+
+
+def cpu_baseline(ref, view_indices, target_seconds):
+    """Whole views of the step, one after the other, until `target_seconds` of CPU time have been spent."""
+    ref.render_view(view_indices[0])            # warm-up: shader JIT, page-in (the reference's protocol has one too)
+    samples, views, dt = 0, 0, 0.0
     for k in view_indices:
-        _, _, st = oracle.render(vol, turntable_camera(k), light, config, lut, args.width, args.height)
-        samples += st["samples"]
+        sec, n = ref.render_view(k)
+        samples += n if n is not None else ref.samples_of(k)
+        dt += sec
         views += 1
-        if time.perf_counter() - t0 >= target_seconds:
+        if dt >= target_seconds:
             break
-    dt = time.perf_counter() - t0
     return {
-        "value": samples / dt / 1e9, "unit": "Gsamples/s", "cores": oracle.num_threads(), "kind": "port",
+        "value": samples / dt / 1e9, "unit": "Gsamples/s", "cores": ref.cores, "kind": ref.kind,
         "sample": f"{views} whole views of the step (turntable views {view_indices[0]}..{view_indices[views - 1]}, "
-                  f"{samples} samples) in {dt:.2f} s; CPU restatement of the reference shader "
-                  f"(oracle/pyvr_oracle.c, OpenMP), llvmpipe/moderngl unavailable in this image",
+                  f"{samples} samples) in {dt:.2f} s after one warm-up view; {ref.what}",
         "seconds": dt, "frames_per_s": views / dt,
     }
 
@@ -194,52 +272,45 @@ def run_reference(args, rank):
     """--impl reference: the CPU path on rank 0 only."""
     if rank != 0:
         return
+    cores = use_all_host_threads()
     import oracle
-    from pyvr_b200 import Volume
 
     data, light, config, lut = scene(args.size)
     normals = oracle.normals(data)   # the reference's compute_normal_volume, restated (bit-exact vs numpy)
-    vol = Volume(data=data, normals=normals, min_bounds=np.array([-1, -1, -1], np.float32),
-                 max_bounds=np.array([1, 1, 1], np.float32))
+    ref = CpuReference(args, data, normals, light, config, lut, args.reference_backend)
     per_step = args.views_per_step
-    # bounded sample: the first `n_sample` WHOLE views of each step's 12 (whole views keep all host threads busy;
-    # a few rows per view would not), sized from one calibration view for about 3 s of CPU time per step
-    t0 = time.perf_counter()
-    oracle.render(vol, turntable_camera(0), light, config, lut, args.width, args.height)
-    t_view = time.perf_counter() - t0
-    n_sample = int(min(per_step, max(1, round(3.0 / max(t_view, 1e-6)))))
-
-    def step(s):
-        total = 0
-        for k in step_view_indices(s, 0, 1, per_step)[:n_sample]:
-            _, _, st = oracle.render(vol, turntable_camera(k), light, config, lut, args.width, args.height)
-            total += st["samples"]
-        return total
-
-    for s in range(args.warmup):
-        step(s)
-    t0 = time.perf_counter()
-    samples = sum(step(args.warmup + s) for s in range(args.steps))
-    dt = time.perf_counter() - t0
-    value = samples / dt / 1e9
-    sample = (f"the first {n_sample} whole views of each step's {per_step}; CPU restatement of the reference shader "
-              "(oracle/, C + OpenMP); the reference's ModernGL path cannot run here (no moderngl, no OpenGL driver)")
+    # one step = the first whole view of the GPU arm's step (a bounded sample: 1 of `per_step` views)
+    ks = [step_view_indices(s, 0, 1, per_step)[0] for s in range(args.warmup + args.steps)]
+    for k in ks[:args.warmup]:
+        ref.render_view(k)
+    dt, samples = 0.0, 0
+    t_wall = time.perf_counter()
+    for k in ks[args.warmup:]:
+        sec, n = ref.render_view(k)
+        dt += sec
+        samples += n if n is not None else 0
+    wall = time.perf_counter() - t_wall
+    if ref.gl is not None:                      # counted outside the timed region
+        samples = sum(ref.samples_of(k) for k in ks[args.warmup:])
+    value = samples / wall / 1e9
+    sample = (f"1 whole view of each step's {per_step} (turntable views {ks[args.warmup]}, {ks[args.warmup] + per_step}, ...); "
+              + ref.what)
     line = {
         "impl": "reference", "metric": "ray-march throughput", "value": value, "unit": "Gsamples/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-        "frames_per_s": args.steps * n_sample / dt,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3,
+        "frames_per_s": args.steps / wall,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, stride_note=f"{n_sample} of {per_step} views per step"),
-        "cpu_baseline": {"value": value, "unit": "Gsamples/s", "cores": oracle.num_threads(), "kind": "port",
-                         "sample": sample},
+        "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": "Gsamples/s", "cores": ref.cores, "kind": ref.kind, "sample": sample,
+                         "host_cores": cores},
         "e2e": {"value": value, "unit": "Gsamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args, stride_note=None):
-    cfg = {
+def workload_config(args):
+    return {
         "workload": f"C3: synthetic {args.size}^3 f32 double_sphere + normals, bounds +-1, {args.width}x{args.height}, "
                     "high_quality (step 0.005, 1000 steps), 360-view turntable (el 30 deg, d 3), "
                     "directional light, viridis + linear(0,0.1)",
@@ -250,13 +321,20 @@ def workload_config(args, stride_note=None):
         "empty_space_skipping": not args.no_ess,
         "sampling": "texture unit, hardware trilinear (8-bit weights)" if getattr(args, "hwtex", False) else "binary32 software trilinear",
     }
-    if stride_note:
-        cfg["sample"] = stride_note
-    return cfg
 
 
-def time_normals_kernel(torch, _cabi, data, device):
-    """K2 on device-resident buffers: best of 5 launches after a warm-up (CUDA events inside the C ABI call)."""
+# --------------------------------------------------------------------------------------------------
+# K2: compute_normal_volume
+# --------------------------------------------------------------------------------------------------
+def numpy_normals(volume):
+    """The reference's compute_normal_volume (pyvr/datasets/synthetic.py:118-122) as numpy evaluates it."""
+    grad = np.stack(np.gradient(volume), axis=-1)
+    return (grad / (np.linalg.norm(grad, axis=-1, keepdims=True) + 1e-8)).astype(np.float32)
+
+
+def time_normals(torch, _cabi, data, device, peak):
+    """K2: device-resident kernel time (best of 5 after a warm-up, CUDA events inside the C ABI call) and the
+    host-array-in / host-array-out call a user of the reference makes, next to the reference's numpy function."""
     n0, n1, n2 = data.shape
     d_in = torch.from_numpy(data).cuda(device)
     d_out = torch.empty((n0, n1, n2, 3), dtype=torch.float32, device=d_in.device)
@@ -267,18 +345,54 @@ def time_normals_kernel(torch, _cabi, data, device):
         best = min(best, ms.value)
     del d_in, d_out
     torch.cuda.empty_cache()
-    return best
+    e2e = float("inf")
+    for _ in range(3):
+        t0 = time.perf_counter()
+        normals = _cabi.compute_normals_host(data, device=device)
+        e2e = min(e2e, time.perf_counter() - t0)
+    t0 = time.perf_counter()
+    want = numpy_normals(data)
+    t_numpy = time.perf_counter() - t0
+    ok = bool(np.array_equal(want.view(np.uint32), normals.view(np.uint32)))
+    gbs = data.size * 16 / (best * 1e-3) / 1e9
+    return normals, {
+        "kernel_ms": best, "GB/s": gbs, "frac_of_hbm_peak": gbs / peak, "algorithmic_bytes_per_voxel": 16,
+        "e2e": {"seconds": e2e, "Mvoxels/s": data.size / e2e / 1e6, "api": "compute_normal_volume(host array) -> host array",
+                "h2d_bytes": data.nbytes, "d2h_bytes": data.nbytes * 3},
+        "cpu_baseline": {"seconds": t_numpy, "Mvoxels/s": data.size / t_numpy / 1e6, "kind": "reference",
+                         "what": "numpy restatement of pyvr/datasets/synthetic.py:118-122 (np.gradient, stack, norm), one process"},
+        "e2e_speedup_vs_numpy": t_numpy / e2e, "bit_identical_to_numpy": ok,
+    }
+
+
+def active_texel_bytes(data, lut, entry_bytes):
+    """Bytes of packed texels in ACTIVE macrocells (8^3 voxels whose scalar range can reach a non-zero LUT alpha):
+    what the ESS march can touch per frame (SURVEY.md section 8 d, 'unique brick bytes touched')."""
+    n = data.shape[0]
+    c = n // 8
+    if n % 8 or data.shape != (n, n, n):
+        return None
+    hi = data.reshape(c, 8, c, 8, c, 8).max(axis=(1, 3, 5))
+    for axis in range(3):                                  # +1 apron the upper taps reach
+        nb = np.concatenate([np.take(hi, range(1, c), axis=axis), np.take(hi, [c - 1], axis=axis)], axis=axis)
+        hi = np.maximum(hi, nb)
+    size = lut.shape[0]
+    nz = np.concatenate([[0], np.cumsum(lut[:, 3] != 0)])
+    jh = np.clip(np.floor(hi.astype(np.float64) * size - 0.5) + 1, 0, size - 1).astype(np.int64)
+    active = nz[jh + 1] > 0                                # lower end of every cell of this volume is ~0
+    return int(active.sum()) * 512 * entry_bytes, float(active.mean())
 
 
 def traffic_per_view(args):
-    """DRAM bytes one view of the march moves, from the committed ncu capture (profiles/r01_traffic.json)."""
-    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    try:
-        table = json.load(open(path))
-        key = f"{args.texels}_{'hwtex_' if args.hwtex else ''}{'dense' if args.no_ess else 'ess'}"
-        return float(table["c3_dram_bytes_per_view"][key])
-    except Exception:
-        return None
+    """DRAM bytes one view of the march moves, from the committed ncu capture (profiles/r02_traffic.json)."""
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            table = json.load(open(os.path.join(ROOT, "profiles", name)))
+            key = f"{args.texels}_{'hwtex_' if args.hwtex else ''}{'dense' if args.no_ess else 'ess'}"
+            return float(table["c3_dram_bytes_per_view"][key]), name
+        except Exception:
+            continue
+    return None, None
 
 
 def main():
@@ -311,15 +425,16 @@ def main():
     from pyvr_b200 import Volume
     from pyvr_b200.cuda_renderer import VolumeRenderer, _cabi
 
+    peak, peak_src = measured_peak_gbs()
     t_setup = time.perf_counter()
     renderer_kw = dict(device=local_rank, texel_format=args.texels, empty_space_skipping=not args.no_ess,
                        hardware_filtering=args.hwtex)
+    normals_info = None
     if world == 1:
         # host pipeline, as a user of the reference would: create_sample_volume -> compute_normal_volume (K2 on
         # the GPU) -> Volume -> load_volume.  The host arrays also feed the CPU baseline.
         data, light, config, lut = scene(args.size)
-        normals, _ = _cabi.compute_normals_host(data, device=local_rank, return_ms=True)   # K2 (first launch: cold)
-        normals_ms = time_normals_kernel(torch, _cabi, data, local_rank)
+        normals, normals_info = time_normals(torch, _cabi, data, local_rank, peak)
         vol = Volume(data=data, normals=normals, min_bounds=np.array([-1, -1, -1], np.float32),
                      max_bounds=np.array([1, 1, 1], np.float32))
         renderer = VolumeRenderer(args.width, args.height, config=config, light=light, **renderer_kw)
@@ -333,11 +448,15 @@ def main():
         light, config = Light.directional([1, -1, 0]), RenderConfig.high_quality()
         lut = build_rgba_lut(ColorTransferFunction.from_colormap("viridis"), OpacityTransferFunction.linear(0.0, 0.1))
         renderer = VolumeRenderer(args.width, args.height, config=config, light=light, **renderer_kw)
-        normals_ms = renderer.generate_volume(args.size, "double_sphere", (-1, -1, -1), (1, 1, 1))
+        normals_info = {"device_generation_ms": renderer.generate_volume(args.size, "double_sphere", (-1, -1, -1), (1, 1, 1))}
     renderer.set_lut(lut)
     stream = torch.cuda.Stream()   # non-default: the library treats stream 0 as "use the context's own stream"
     renderer.set_stream(stream.cuda_stream)
     setup_s = time.perf_counter() - t_setup
+
+    # roofline denominators measured on this GPU, now (csrc/bandwidth.cu)
+    l1_gbs = _cabi.measure_cache_bandwidth(1, local_rank)
+    l2_gbs = _cabi.measure_cache_bandwidth(2, local_rank)
 
     per_step = args.views_per_step
     frame_bytes = args.width * args.height * 4
@@ -367,9 +486,9 @@ def main():
         return float(t.item())
 
     # ---------------- device-resident pass: `value` + roofline -----------------------------------
-    def resident_step(s):
-        renderer.render_batch(views=views[s], device_ptr=d_frames.data_ptr())
-        return renderer.stats
+    def resident_step(s, r=renderer):
+        r.render_batch(views=views[s], device_ptr=d_frames.data_ptr())
+        return r.stats
 
     for s in range(args.warmup):
         resident_step(s)
@@ -409,42 +528,59 @@ def main():
     e2e_value = sum_over_ranks(float(e2e_samples)) / (e2e_ms * 1e-3) / 1e9
     checksum = int(pinned.array[::4099].astype(np.uint64).sum())
 
-    # ---------------- alternatives (N = 1 only): same views, other texel storage / sampler, device-resident.
-    # Not the headline: the headline is binary32 texels + binary32 software trilinear (the north star's
-    # primary path); these are the configurations the north star lists as allowed when within tolerance.
-    alternatives = {}
-    if world == 1 and not args.no_alternatives and not args.hwtex and args.texels == "f32":
+    # ---------------- side measurements (N = 1 only), a few steps each, device-resident:
+    # the dense march (no empty-space skipping) for the roofline of the fetch path itself, and the storage /
+    # sampler alternatives the north star allows when within tolerance.  Not the headline: the headline is
+    # binary32 texels + binary32 software trilinear + exact skipping.
+    def side_run(kw, steps):
+        r = VolumeRenderer(args.width, args.height, config=config, light=light, device=local_rank, **kw)
+        r.load_volume(vol)
+        r.set_lut(lut)
+        r.set_stream(stream.cuda_stream)
+        resident_step(0, r)
+        torch.cuda.synchronize()
+        e0.record(stream)
+        n_s = n_f = n_l = 0
+        k_ms = 0.0
+        for s_ in range(steps):
+            st_ = resident_step(args.warmup + s_, r)
+            n_s, n_f, n_l, k_ms = n_s + st_["samples"], n_f + st_["samples_fetched"], n_l + st_["kernel_launches"], k_ms + st_["kernel_ms"]
+        e1.record(stream)
+        torch.cuda.synchronize()
+        t_ms = e0.elapsed_time(e1)
+        r.close()
+        return {"value": n_s / (t_ms * 1e-3) / 1e9, "unit": "Gsamples/s", "frames_per_s": steps * per_step / (t_ms * 1e-3),
+                "fetched_Gsamples/s": n_f / (k_ms * 1e-3) / 1e9, "kernel_ms_per_view": k_ms / (steps * per_step)}
+
+    alternatives, dense = {}, None
+    if world == 1 and not args.no_alternatives and not args.hwtex and args.texels == "f32" and not args.no_ess:
+        side_steps = max(1, min(args.steps, 3))
+        dense = side_run(dict(texel_format="f32", empty_space_skipping=False), 1)
         for name, kw in (("f16x4 texels, software trilinear", dict(texel_format="f16")),
                          ("f16x4 texels, texture-unit trilinear (hwtex)", dict(texel_format="f16", hardware_filtering=True))):
-            alt = VolumeRenderer(args.width, args.height, config=config, light=light, device=local_rank,
-                                 empty_space_skipping=not args.no_ess, **kw)
-            alt.load_volume(vol)
-            alt.set_lut(lut)
-            alt.set_stream(stream.cuda_stream)
-            for s_ in range(args.warmup):
-                alt.render_batch(views=views[s_], device_ptr=d_frames.data_ptr())
-            torch.cuda.synchronize()
-            e0.record(stream)
-            alt_samples = 0
-            for s_ in range(args.warmup, total_steps):
-                alt.render_batch(views=views[s_], device_ptr=d_frames.data_ptr())
-                alt_samples += alt.stats["samples"]
-            e1.record(stream)
-            torch.cuda.synchronize()
-            alt_ms = e0.elapsed_time(e1)
-            alternatives[name] = {"value": alt_samples / (alt_ms * 1e-3) / 1e9, "unit": "Gsamples/s",
-                                  "frames_per_s": args.steps * per_step / (alt_ms * 1e-3)}
-            alt.close()
+            alternatives[name] = side_run(dict(empty_space_skipping=True, **kw), side_steps)
 
+    line = None
     if rank == 0:
         bytes_per_sample = BYTES_PER_SAMPLE_F32 if args.texels == "f32" else BYTES_PER_SAMPLE_F16
-        peak, peak_src = measured_peak_gbs()
         launch_ms = kernel_ms / max(launches, 1)
-        achieved = (fetched / max(launches, 1)) * bytes_per_sample / (launch_ms * 1e-3) / 1e9
-        views_per_launch = per_step if per_step <= 16 else 16
-        per_view = traffic_per_view(args)
+        fetched_per_launch = fetched / max(launches, 1)
+        achieved = fetched_per_launch * bytes_per_sample / (launch_ms * 1e-3) / 1e9
+        views_per_launch = per_step / max(launches / max(args.steps, 1), 1)
+        per_view, traffic_file = traffic_per_view(args)
         sm_mhz = clocks.summary().get("sm_mhz") or 1965.0
-        l1_peak = 148 * 128 * sm_mhz * 1e6 / 1e9      # one 128-byte L1 wavefront per SM per clock
+        l1_nominal = 148 * 128 * sm_mhz * 1e6 / 1e9      # one 128-byte load-return wavefront per SM per clock
+        frames_per_s_kernel = views_per_launch / (launch_ms * 1e-3)
+        hbm = None
+        if data is not None:
+            got = active_texel_bytes(data, lut, 32 if args.texels == "f32" else 16)
+            if got is not None:
+                unique = got[0] if not args.no_ess else data.size * (32 if args.texels == "f32" else 16)
+                hbm_achieved = (unique + frame_bytes) * frames_per_s_kernel / 1e9
+                hbm = {"achieved": hbm_achieved, "peak": peak, "unit": "GB/s", "frac": hbm_achieved / peak,
+                       "unique_texel_bytes_per_frame": unique, "active_cell_fraction": got[1], "peak_source": peak_src,
+                       "note": "SURVEY.md section 8(d): (unique brick bytes touched per frame + W*H*4) x frames/s of the kernel / "
+                               "HBM copy rate; unique = packed z-pair entries (32 B per voxel) of the active 8^3 macrocells"}
         line = {
             "metric": "ray-march throughput", "value": value, "unit": "Gsamples/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
@@ -452,48 +588,65 @@ def main():
             "config": workload_config(args),
             "frames_per_s": frames / (ms * 1e-3),
             "samples_per_frame": all_samples / frames,
+            "timed_region_s": ms * 1e-3,
             "e2e": {"value": e2e_value, "unit": "Gsamples/s", "frames_per_s": frames / (e2e_ms * 1e-3),
                     "h2d_bytes_per_step": world * per_step * ctypes.sizeof(_cabi.View),
                     "d2h_bytes_per_step": world * per_step * frame_bytes,
                     "api": "VolumeRenderer.render_batch(views, out=pinned host buffer)", "frame_checksum": checksum},
             "gpu_launches": int(launches),
             "roofline": {
-                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                # the binding unit of this gather kernel is the SM's L1 load-return path: every lane must receive its
+                # 8 texels (128 B) per sample through it, whatever the hit rate
+                "bound": "l1", "achieved": achieved, "peak": l1_gbs, "unit": "GB/s", "frac": achieved / l1_gbs,
                 "traffic": per_view * views_per_launch if per_view else None,
-                "traffic_source": "profiles/r01_traffic.json (ncu dram__bytes_read+write of a 1-view launch x views per launch)",
-                "peak_source": peak_src, "kernel": "march_kernel<fast>",
-                "kernel_ms_per_launch": launch_ms, "views_per_launch": views_per_launch,
-                "l1": {"bound": "l1tex data stage", "achieved": achieved, "peak": l1_peak, "unit": "GB/s",
-                       "frac": achieved / l1_peak,
-                       "note": "same algorithmic bytes against 148 SMs x 128 B/clk at the sampled SM clock: the unit "
-                               "that actually binds this gather kernel (ncu: l1tex data-stage 71-76 % busy, issue slots 58-68 %, DRAM 16-24 %)"},
+                "traffic_source": f"profiles/{traffic_file} (ncu dram__bytes_read+write of a 1-view launch x views per launch)" if per_view else None,
+                "peak_source": "measured live: pyvr_cuda_measure_cache_bandwidth(level 1) -- coalesced LDG.128 hitting L1, "
+                               "bytes delivered to registers / CUDA-event time (csrc/bandwidth.cu)",
+                "peak_nominal": l1_nominal, "frac_of_nominal": achieved / l1_nominal,
+                "kernel": "march_kernel<fast, f32x4 z-pair>", "kernel_ms_per_launch": launch_ms, "views_per_launch": views_per_launch,
+                "algorithmic_bytes_per_sample": bytes_per_sample,
+                "samples_fetched_per_launch": fetched_per_launch,
+                "samples_reference_per_launch": samples / max(launches, 1),
+                "fetched_Gsamples_per_s": fetched_per_launch / (launch_ms * 1e-3) / 1e9,
+                "kernel_share_of_step": kernel_ms / ms if world == 1 else None,
+                "l2": {"achieved": achieved, "peak": l2_gbs, "unit": "GB/s", "frac": achieved / l2_gbs,
+                       "peak_source": "measured live: pyvr_cuda_measure_cache_bandwidth(level 2) -- coalesced LDG.128.cg over 64 MiB",
+                       "note": "SURVEY.md section 8(d)'s L2 form: algorithmic gather bytes against the L2->SM read bandwidth; L1 absorbs "
+                               "the 8x gather amplification, so this fraction may exceed 1 and L2 is not the binding unit"},
+                "hbm": hbm,
                 "dram": ({"achieved": per_view * views_per_launch / (launch_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                           "frac": per_view * views_per_launch / (launch_ms * 1e-3) / 1e9 / peak,
-                          "note": "measured DRAM traffic per launch / kernel time: each packed line comes from HBM about "
-                                  "once per view, so HBM is far from binding"} if per_view else None),
-                "algorithmic_bytes_per_sample": bytes_per_sample,
-                "samples_fetched_per_launch": fetched / max(launches, 1),
-                "samples_reference_per_launch": samples / max(launches, 1),
-                "kernel_share_of_step": kernel_ms / ms if world == 1 else None,
-                "note": "achieved = fetched samples x 8 texels x texel bytes / march-kernel time.  The gather is served "
-                        "by L1/L2 (each packed line is read from HBM about once per view: `traffic`), so the "
-                        "fraction of the HBM copy rate exceeds 1; see `l1` for the binding unit",
+                          "note": "DRAM traffic ncu measured per launch / kernel time"} if per_view else None),
+                "dense": ({**dense, "achieved": dense["fetched_Gsamples/s"] * bytes_per_sample, "peak": l1_gbs,
+                           "frac": dense["fetched_Gsamples/s"] * bytes_per_sample / l1_gbs,
+                           "note": "same kernel with empty-space skipping off (every in-box sample fetched), 1 step"} if dense else None),
+                "note": "achieved = fetched samples x 8 texels x 16 B / march-kernel time (CUDA events inside the C ABI call, "
+                        "on the launching stream); peak = L1 load-return bandwidth measured on this GPU in this run",
             },
             "clocks": clocks.summary(),
-            "normals_kernel": ({"ms": normals_ms, "GB/s": args.size ** 3 * 16 / (normals_ms * 1e-3) / 1e9,
-                                "frac_of_hbm_peak": args.size ** 3 * 16 / (normals_ms * 1e-3) / 1e9 / peak,
-                                "algorithmic_bytes_per_voxel": 16} if world == 1 else
-                               {"device_generation_ms": normals_ms}),
+            "normals_kernel": normals_info,
             "alternatives": alternatives,
             "setup_s": setup_s,
         }
-        if not args.skip_cpu_baseline and world == 1:
-            line["cpu_baseline"] = cpu_baseline(data, normals, light, config, lut, args,
-                                                step_view_indices(args.warmup, 0, 1, per_step), args.cpu_seconds)
-        print(json.dumps(line), flush=True)
 
+    # ---------------- N > 1: the partitioned configs and their parity, time-boxed ----------------
     renderer.close()
     pinned.close()
+    del d_frames
+    torch.cuda.empty_cache()
+    if world > 1 and not args.no_secondary:
+        import bench_partitioned
+
+        secondary = bench_partitioned.secondary_section(args, rank, world, local_rank, line, args.secondary_seconds)
+        if rank == 0:
+            line.update(secondary)
+    elif rank == 0 and not args.skip_cpu_baseline and world == 1:
+        cores = use_all_host_threads()
+        ref = CpuReference(args, data, normals, light, config, lut, args.reference_backend)
+        line["cpu_baseline"] = cpu_baseline(ref, step_view_indices(args.warmup, 0, 1, per_step), args.cpu_seconds)
+        line["cpu_baseline"]["host_cores"] = cores
+    if rank == 0:
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -22,6 +22,7 @@ assembled RGBA8 frame into pinned host memory on rank 0.
 
 from __future__ import annotations
 
+import argparse
 import ctypes
 import json
 import os
@@ -34,15 +35,15 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 
+def default_c5_size(world):
+    """Edge of the C5 volume for `world` bricks: per-GPU voxels stay at 2048^3 (weak scaling), multiple of 64."""
+    return int(round(2048 * world ** (1 / 3) / 64) * 64)
+
+
 def run(args, rank, world, local_rank):
+    """``bench.py --workload c4|c5``: one JSON line for the partitioned config."""
     import torch
     import torch.distributed as dist
-
-    import bench
-    from pyvr_b200 import (Camera, ColorTransferFunction, Light, OpacityTransferFunction, RenderConfig,
-                           build_rgba_lut)
-    from pyvr_b200 import multi_gpu as mg
-    from pyvr_b200.cuda_renderer import VolumeRenderer, _cabi
 
     if args.impl == "reference":
         if rank == 0:
@@ -54,10 +55,31 @@ def run(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    line = measure(args, rank, world, local_rank, args.workload, args.steps, args.warmup, args.size, args.width, args.height)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
 
+
+def measure(args, rank, world, local_rank, workload, steps, warmup, size=None, width=None, height=None):
+    """Measure one partitioned config on an initialised process group.  Returns the JSON-able line on rank 0,
+    None elsewhere."""
+    import torch
+    import torch.distributed as dist
+
+    import bench
+    from pyvr_b200 import (Camera, ColorTransferFunction, Light, OpacityTransferFunction, RenderConfig,
+                           build_rgba_lut)
+    from pyvr_b200 import multi_gpu as mg
+    from pyvr_b200.cuda_renderer import VolumeRenderer, _cabi
+
+    args = argparse.Namespace(**vars(args))
+    args.workload, args.steps, args.warmup = workload, steps, warmup
+    args.size, args.width, args.height = size, width, height     # None = the config's own (2048 / 2048*cbrt(N), 3840x2160)
     c5 = args.workload == "c5"
     if args.size is None:
-        args.size = int(round(2048 * round(world ** (1 / 3)))) if c5 else 2048
+        args.size = default_c5_size(world) if c5 else 2048
     width, height = args.width or 3840, args.height or 2160
     n_pixels = width * height
     config = RenderConfig.high_quality() if c5 else RenderConfig.ultra_quality()
@@ -78,7 +100,7 @@ def run(args, rank, world, local_rank):
     if c5 and world > 1:
         brick = mg.brick_of_rank(shape, rank, world)
         gen_ms = renderer.generate_volume(args.size, "double_sphere", bmin, bmax, brick=brick)
-        session = mg.SortLastSession(shape, bmin, bmax, n_pixels, device=local_rank, exchange=args.exchange)
+        session = mg.SortLastSession(shape, bmin, bmax, n_pixels, device=local_rank, exchange=args.exchange, renderer=renderer)
         stored = brick.dims
     else:
         brick, session = None, None
@@ -205,11 +227,154 @@ def run(args, rank, world, local_rank):
             "volume_generation": {"ms": gen_ms, "voxels_per_gpu": voxels, "Gvoxels/s": voxels / (gen_ms * 1e-3) / 1e9},
             "setup_s": setup_s,
         }
-        print(json.dumps(line), flush=True)
+    else:
+        line = None
 
     if session is not None:
         session.close()
     renderer.close()
     pinned.close()
-    if world > 1:
-        dist.destroy_process_group()
+    del frame
+    torch.cuda.empty_cache()
+    return line
+
+
+def parity_check(rank, world, local_rank):
+    """The multi-process paths against the single-GPU frame, on C1's volume (128^3 double_sphere + normals, balanced,
+    isometric view) at 400x300: (1) image tiles: reduce(SUM) of the per-rank frames == the single-GPU frame, bit for
+    bit; (2) sort-last bricks + binary swap (p2p and nccl exchange): within max |delta| <= 3/255, >= 99.9 % of the
+    pixels within 1/255 (the merge clips saturating rays to alpha 0.99); brick sample counts
+    add up to the single-GPU count; (3) relay: bit-identical; (4) on rank 0 the single-GPU frame itself against the
+    CPU oracle within BASELINE.json's tolerance.  Returns a dict on rank 0, None elsewhere."""
+    import torch
+    import torch.distributed as dist
+
+    from pyvr_b200 import (Camera, ColorTransferFunction, Light, OpacityTransferFunction, RenderConfig, Volume,
+                           build_rgba_lut, compute_normal_volume, create_sample_volume)
+    from pyvr_b200 import multi_gpu as mg
+    from pyvr_b200.cuda_renderer import VolumeRenderer, _cabi
+
+    W, H = 400, 300
+    data = create_sample_volume(128, "double_sphere")
+    vol = Volume(data=data, normals=compute_normal_volume(data))
+    light, cfg = Light.directional([1, -1, 0]), RenderConfig.balanced()
+    lut = build_rgba_lut(ColorTransferFunction.from_colormap("viridis"), OpacityTransferFunction.linear(0.0, 0.3))
+    cam = Camera.isometric_view(distance=3.0)
+    position, _ = cam.get_camera_vectors()
+    out = {"scene": "C1 volume (128^3 double_sphere + normals), balanced, isometric view, 400x300", "ranks": world}
+
+    def frame_of(ptr_or_tensor):
+        if isinstance(ptr_or_tensor, int):
+            torch.cuda.synchronize()
+            host = np.empty(W * H * 4, np.uint8)
+            _cabi.check(_cabi.lib().pyvr_cuda_memcpy(local_rank, host.ctypes.data, ctypes.c_void_p(ptr_or_tensor), W * H * 4, 2, None))
+            return host.reshape(H, W, 4)
+        return ptr_or_tensor.cpu().numpy().reshape(H, W, 4)
+
+    def metrics(got, want):
+        d = np.abs(got.astype(np.int32) - want.astype(np.int32))
+        return {"max_abs": int(d.max()), "frac_within_1": float((d <= 1).all(axis=-1).mean()),
+                "frac_identical": float((d == 0).all(axis=-1).mean())}
+
+    with VolumeRenderer(W, H, config=cfg, light=light, device=local_rank) as r:
+        r.set_stream(torch.cuda.current_stream().cuda_stream)
+        r.load_volume(vol)
+        r.set_camera(cam)
+        r.set_lut(lut)
+        want = np.frombuffer(r.render(), np.uint8).reshape(H, W, 4).copy()
+        want_samples = r.stats["samples"]
+        # (1) image tiles
+        r.set_pixel_shard(rank, world)
+        tiles = torch.zeros(H * W * 4, dtype=torch.uint8, device="cuda")
+        r.render_to_device(tiles.data_ptr())
+        mg.reduce_tile_frames(tiles, dst=0)
+        r.set_pixel_shard(0, 1)
+        if rank == 0:
+            out["tiles_bit_identical"] = bool(np.array_equal(frame_of(tiles), want))
+        # (2) sort-last bricks, both exchange paths; (3) relay
+        if world & (world - 1) == 0:
+            b = mg.brick_of_rank(data.shape, rank, world)
+            r.load_brick(vol.data[b.slices()], vol.normals[b.slices()], data.shape, b.origin, b.own_lo, b.own_hi,
+                         vol.min_bounds, vol.max_bounds)
+            r.set_camera(cam)
+            r.set_lut(lut)
+            for exchange in ("p2p", "nccl"):
+                session = mg.SortLastSession(data.shape, vol.min_bounds, vol.max_bounds, W * H, device=local_rank, exchange=exchange, renderer=r)
+                for _ in range(2):                   # twice: buffers are reused across frames
+                    r.render_accum_to_device(session.image_ptr())
+                    piece_range, piece = session.composite(position)
+                    frame = session.gather_rgba8(piece_range, piece)
+                samples = torch.tensor([r.stats["samples"]], dtype=torch.int64, device="cuda")
+                dist.all_reduce(samples)
+                if rank == 0:
+                    m = metrics(frame_of(frame), want)
+                    m["ok"] = bool(m["max_abs"] <= 3 and m["frac_within_1"] >= 0.999)
+                    m["brick_samples_add_up"] = bool(int(samples.item()) == want_samples)
+                    out[f"sort_last_{exchange}"] = m
+                session.close()
+            relay = mg.RelaySession(data.shape, vol.min_bounds, vol.max_bounds, W * H, device=local_rank)
+            relay_frame = relay.render(r, position)
+            flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+            if relay_frame is not None:              # the last rank of the visibility order holds the frame
+                flag[0] = int(np.array_equal(frame_of(relay_frame), want)) + 1
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+            if rank == 0:
+                out["relay_bit_identical"] = bool(int(flag.item()) == 2)
+    if rank != 0:
+        return None
+    try:   # the checker: single-GPU frame vs the CPU oracle (BASELINE tolerance)
+        import oracle
+
+        ref, _, _ = oracle.render(vol, cam, light, cfg, lut, W, H)
+        d = np.abs(want.astype(np.int32) - ref.astype(np.int32))
+        mse = float(np.mean((want.astype(np.float64) - ref.astype(np.float64)) ** 2))
+        out["single_gpu_vs_oracle"] = {"max_abs": int(d.max()), "frac_within_2": float((d <= 2).all(axis=-1).mean()),
+                                       "psnr_db": float("inf") if mse == 0 else float(10 * np.log10(255.0 ** 2 / mse))}
+    except Exception as e:
+        out["single_gpu_vs_oracle"] = {"error": f"{type(e).__name__}: {e}"}
+    checks = [out.get("tiles_bit_identical", False)]
+    if world & (world - 1) == 0:
+        checks += [out["sort_last_p2p"]["ok"], out["sort_last_nccl"]["ok"], out["relay_bit_identical"]]
+    out["all_ok"] = bool(all(checks))
+    return out
+
+
+def secondary_section(args, rank, world, local_rank, line, seconds):
+    """N > 1: C4 (image tiles) and C5 (sort-last) lines plus the parity check, inside a time box.  A watchdog
+    thread makes sure the main line is still printed (and every rank exits 0) if a collective of this section
+    hangs.  Returns {"secondary": {...}, "parity_check": {...}} on rank 0."""
+    import threading
+
+    result = {"secondary": {}, "parity_check": None}
+
+    def give_up():
+        if rank == 0:
+            result["secondary"]["error"] = f"secondary section exceeded its {seconds:.0f} s time box; partial results kept"
+            line.update(result)
+            print(json.dumps(line), flush=True)
+        os._exit(0)
+
+    dog = threading.Timer(seconds, give_up)
+    dog.daemon = True
+    dog.start()
+    t0 = time.perf_counter()
+    try:
+        try:
+            result["parity_check"] = parity_check(rank, world, local_rank)
+        except Exception as e:      # a failure here is deterministic (same on every rank): report and go on
+            result["parity_check"] = {"error": f"{type(e).__name__}: {e}"}
+        for workload in ("c4", "c5"):
+            if workload == "c5" and world & (world - 1):
+                continue
+            try:
+                got = measure(args, rank, world, local_rank, workload, steps=8, warmup=2)
+                if rank == 0:
+                    keep = ("value", "unit", "ms_per_step", "frames_per_s", "samples_per_frame", "scaling", "config", "e2e",
+                            "roofline", "clocks", "volume_generation", "steps", "warmup", "n_gpus", "balance")
+                    result["secondary"][workload] = {k: got[k] for k in keep if k in got}
+            except Exception as e:
+                result["secondary"][workload] = {"error": f"{type(e).__name__}: {e}"}
+        result["secondary"]["seconds"] = time.perf_counter() - t0
+    finally:
+        dog.cancel()
+    return result if rank == 0 else None

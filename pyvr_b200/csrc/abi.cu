@@ -188,13 +188,13 @@ void fill_volume_desc(pyvr_ctx *c, const int local[3], const int global[3], cons
         v.ncell[a] = (v.n[a] + 7) / 8;
     }
     // padded pitches (common.cuh): rows of n[2] + 2 entries, planes of n[1] + 2 rows, rounded up to the residue
-    // that rotates the L1 bank of texel (ix, iy, iz) by ix + 3*iy entries.  Measured best in round 1 among the
-    // linear maps tried, including the ones with the longest shortest collision vector (tools/swizzle_search.py),
-    // which were 10 % slower on the dense march: what matters is that the texels one quarter-warp touches -- a
-    // short run along the image-row direction -- spread over the banks.
+    // that rotates the L1 bank of texel (ix, iy, iz) by 3*ix + iy entries.  All 16 residue pairs were measured on
+    // C3 with z-pair entries (4 per line; profiles/r02_layout_ab.txt): no rotation 320 Gsamples/s, (1,3) -- the
+    // round-1 slot swizzle -- 428, (3,1) 449; what matters is that the texels one quarter-warp touches -- a short
+    // run along the image-row direction -- spread over the banks.
     v.pair = c->use_pair ? 1 : 0;
     const int slots = 128 / entry_bytes(c->half_texels, v.pair);
-    int rx = 1, ry = 3;
+    int rx = 3, ry = 1;
     if (!c->swizzle) rx = ry = 0;
     else {
         const char *env = getenv("PYVR_CUDA_SWZ");   // "x,y" override for experiments
@@ -452,7 +452,19 @@ int pyvr_cuda_destroy(pyvr_ctx *c) {
 
 int pyvr_cuda_set_stream(pyvr_ctx *c, void *cuda_stream) {
     if (!c) return fail(PYVR_ERR_INVALID, "ctx is NULL");
-    c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+    cudaStream_t next = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+    if (next != c->stream) {
+        // work still pending on the old stream (uploads, cell classification, a march) stays ordered before
+        // whatever is enqueued on the new one
+        DeviceGuard guard(c->device);
+        cudaEvent_t ev = nullptr;
+        CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        cudaError_t e = cudaEventRecord(ev, c->stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(next, ev, 0);
+        cudaEventDestroy(ev);
+        CU(e);
+    }
+    c->stream = next;
     return PYVR_OK;
 }
 
@@ -475,6 +487,25 @@ int pyvr_cuda_set_option(pyvr_ctx *c, const char *key, int value) {
 
 namespace {
 
+// Device buffers of a volume whose c->vol / c->texel_bytes / c->n_cells are set.  On failure nothing stays allocated.
+int alloc_volume_buffers(pyvr_ctx *c) {
+    cudaError_t e = cudaMalloc(&c->texels, c->texel_bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&c->cell_minmax, c->n_cells * sizeof(float2));
+    if (e == cudaSuccess) e = cudaMalloc(&c->cell_dist, c->n_cells);
+    if (e == cudaSuccess) e = cudaMalloc(&c->cell_scratch, c->n_cells);
+    if (e == cudaSuccess) e = cudaMalloc(&c->active_box, 6 * sizeof(int));
+    // row / plane padding is never read; keep it defined
+    if (e == cudaSuccess) e = cudaMemsetAsync(c->texels, 0, c->texel_bytes, c->stream);
+    if (e != cudaSuccess) {
+        free_volume(c);
+        CU(e);
+    }
+    c->vol.texels = c->texels;
+    c->vol.cell_dist = c->cell_dist;
+    c->vol.active_box = c->active_box;
+    return PYVR_OK;
+}
+
 // Shared tail of upload_volume / upload_brick: allocate, stage, pack, build the macrocell grid.
 // c->vol (dims, ownership, bounds) and c->half_texels are already set.
 int upload_packed(pyvr_ctx *c, const float *scalar, const float *normals, int src_is_device) {
@@ -483,35 +514,32 @@ int upload_packed(pyvr_ctx *c, const float *scalar, const float *normals, int sr
     const size_t n_tex = texel_count(c);
     c->texel_bytes = n_tex * entry_bytes(c->half_texels, c->vol.pair);
     c->n_cells = (size_t)v.ncell[0] * v.ncell[1] * v.ncell[2];
-    CU(cudaMalloc(&c->texels, c->texel_bytes));
-    CU(cudaMalloc(&c->cell_minmax, c->n_cells * sizeof(float2)));
-    CU(cudaMalloc(&c->cell_dist, c->n_cells));
-    CU(cudaMalloc(&c->cell_scratch, c->n_cells));
-    CU(cudaMalloc(&c->active_box, 6 * sizeof(int)));
-    CU(cudaMemsetAsync(c->texels, 0, c->texel_bytes, c->stream));   // row / plane padding is never read; keep it defined
-    c->vol.texels = c->texels;
-    c->vol.cell_dist = c->cell_dist;
-    c->vol.active_box = c->active_box;
+    int rc = alloc_volume_buffers(c);
+    if (rc != PYVR_OK) return rc;
 
+    // host sources go through device staging buffers; one exit frees them whatever fails (an out-of-memory here
+    // must not leak multi-GB buffers for the life of the process), and a failed upload leaves no volume behind
     const float *d_scalar = scalar, *d_normals = normals;
     float *stage_s = nullptr, *stage_n = nullptr;
+    cudaError_t e = cudaSuccess;
     if (!src_is_device) {
-        CU(cudaMalloc(&stage_s, voxels * sizeof(float)));
-        CU(cudaMemcpyAsync(stage_s, scalar, voxels * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        e = cudaMalloc(&stage_s, voxels * sizeof(float));
+        if (e == cudaSuccess) e = cudaMemcpyAsync(stage_s, scalar, voxels * sizeof(float), cudaMemcpyHostToDevice, c->stream);
         d_scalar = stage_s;
-        if (normals) {
-            cudaError_t e = cudaMalloc(&stage_n, voxels * 3 * sizeof(float));
-            if (e != cudaSuccess) { cudaFree(stage_s); CU(e); }
-            CU(cudaMemcpyAsync(stage_n, normals, voxels * 3 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        if (e == cudaSuccess && normals) {
+            e = cudaMalloc(&stage_n, voxels * 3 * sizeof(float));
+            if (e == cudaSuccess) e = cudaMemcpyAsync(stage_n, normals, voxels * 3 * sizeof(float), cudaMemcpyHostToDevice, c->stream);
             d_normals = stage_n;
         }
     }
-    cudaError_t e = launch_pack_texels(d_scalar, d_normals, c->vol, c->half_texels, c->stream);
+    if (e == cudaSuccess) e = launch_pack_texels(d_scalar, d_normals, c->vol, c->half_texels, c->stream);
     if (e == cudaSuccess) e = launch_fill_apron(c->vol, c->half_texels, c->stream);
     if (e == cudaSuccess) e = launch_cell_minmax(c->vol, c->half_texels, c->cell_minmax, c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    else cudaStreamSynchronize(c->stream);
     cudaFree(stage_s);
     cudaFree(stage_n);
+    if (e != cudaSuccess) free_volume(c);
     CU(e);
     c->have_volume = true;
     return classify_cells(c);
@@ -604,15 +632,8 @@ int pyvr_cuda_generate_volume(pyvr_ctx *c, int shape, int size, const int local_
     const size_t n_tex = texel_count(c);
     c->texel_bytes = n_tex * entry_bytes(c->half_texels, c->vol.pair);
     c->n_cells = (size_t)v.ncell[0] * v.ncell[1] * v.ncell[2];
-    CU(cudaMalloc(&c->texels, c->texel_bytes));
-    CU(cudaMalloc(&c->cell_minmax, c->n_cells * sizeof(float2)));
-    CU(cudaMalloc(&c->cell_dist, c->n_cells));
-    CU(cudaMalloc(&c->cell_scratch, c->n_cells));
-    CU(cudaMalloc(&c->active_box, 6 * sizeof(int)));
-    CU(cudaMemsetAsync(c->texels, 0, c->texel_bytes, c->stream));
-    c->vol.texels = c->texels;
-    c->vol.cell_dist = c->cell_dist;
-    c->vol.active_box = c->active_box;
+    int rc = alloc_volume_buffers(c);
+    if (rc != PYVR_OK) return rc;
 
     // slab scratch: about 1 GiB, at least 3 planes
     const size_t plane = (size_t)(v.n[1] + 2) * (size_t)(v.n[2] + 2);
@@ -620,9 +641,9 @@ int pyvr_cuda_generate_volume(pyvr_ctx *c, int shape, int size, const int local_
     if (planes < 3) planes = 3;
     if (planes > (size_t)v.n[0] + 2) planes = (size_t)v.n[0] + 2;
     float *scratch = nullptr;
-    CU(cudaMalloc(&scratch, planes * plane * sizeof(float)));
     cudaEvent_t e0 = nullptr, e1 = nullptr;
-    cudaError_t e = cudaEventCreate(&e0);
+    cudaError_t e = cudaMalloc(&scratch, planes * plane * sizeof(float));
+    if (e == cudaSuccess) e = cudaEventCreate(&e0);
     if (e == cudaSuccess) e = cudaEventCreate(&e1);
     if (e == cudaSuccess) e = cudaEventRecord(e0, c->stream);
     if (e == cudaSuccess) e = launch_synth_volume(c->vol, c->half_texels, shape, size, scratch, planes * plane, c->stream);
@@ -634,6 +655,7 @@ int pyvr_cuda_generate_volume(pyvr_ctx *c, int shape, int size, const int local_
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);
     cudaFree(scratch);
+    if (e != cudaSuccess) free_volume(c);
     CU(e);
     c->have_volume = true;
     return classify_cells(c);

@@ -202,6 +202,9 @@ class CudaVolumeRenderer:
         """``render()`` into a ``(height, width, 4) uint8`` array (pinned or not); no ``bytes`` copy."""
         if out is None:
             out = np.empty((self.height, self.width, 4), dtype=np.uint8)
+        if (not isinstance(out, np.ndarray) or out.dtype != np.uint8 or not out.flags.c_contiguous
+                or not out.flags.writeable or out.nbytes < self.height * self.width * 4):
+            raise ValueError("out must be a writeable C-contiguous uint8 array of at least height*width*4 bytes")
         _cabi.check(self._lib.pyvr_cuda_render(self._ctx, out.ctypes.data, 0))
         return out
 
@@ -222,6 +225,8 @@ class CudaVolumeRenderer:
         Frame k's device->host copy overlaps the march of frame k+1.
         """
         if views is None:
+            if cameras is None:
+                raise ValueError("render_batch needs `cameras` or `views`")
             views = self.make_views(cameras)
         n = len(views)
         if device_ptr is not None:
@@ -229,8 +234,9 @@ class CudaVolumeRenderer:
             return None
         if out is None:
             out = np.empty((n, self.height, self.width, 4), dtype=np.uint8)
-        if out.nbytes < n * self.height * self.width * 4 or not out.flags.c_contiguous:
-            raise ValueError("out must be a C-contiguous buffer of n*height*width*4 bytes")
+        if (not isinstance(out, np.ndarray) or out.dtype != np.uint8 or not out.flags.c_contiguous
+                or not out.flags.writeable or out.nbytes < n * self.height * self.width * 4):
+            raise ValueError("out must be a writeable C-contiguous uint8 buffer of n*height*width*4 bytes")
         _cabi.check(self._lib.pyvr_cuda_render_batch(self._ctx, views, n, out.ctypes.data, 0))
         return out
 

@@ -249,6 +249,7 @@ class RelaySession:
         import torch.distributed as dist
 
         self.torch, self.dist, self.group = torch, dist, group
+        self._bound = None
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         self.shape = tuple(int(s) for s in shape)
         self.min_bounds, self.max_bounds = np.asarray(min_bounds, np.float64), np.asarray(max_bounds, np.float64)
@@ -264,6 +265,7 @@ class RelaySession:
         cam = camera_in_voxels(camera_pos, self.min_bounds, self.max_bounds, self.shape)
         order = relay_order(self.world, self.shape, cam)
         pos = order.index(self.rank)
+        _bind_stream(self, renderer)       # march, send/recv and finalize all in the order of torch's current stream
         if pos > 0:
             self.dist.recv(self.image, src=order[pos - 1], group=self.group)
         self.torch.cuda.current_stream().synchronize()
@@ -287,12 +289,16 @@ class SortLastSession:
     """
 
     def __init__(self, shape, min_bounds, max_bounds, n_pixels: int, *, group=None, device: Optional[int] = None,
-                 exchange: str = "nccl", over: Optional[Callable] = None, termination_alpha: float = 0.99):
+                 exchange: str = "nccl", over: Optional[Callable] = None, termination_alpha: float = 0.99,
+                 renderer=None):
         import torch
         import torch.distributed as dist
 
         self.torch, self.dist = torch, dist
         self.group = group
+        self._bound = None
+        if renderer is not None:
+            _bind_stream(self, renderer)
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         self.shape = tuple(int(s) for s in shape)
         self.min_bounds, self.max_bounds = np.asarray(min_bounds, np.float64), np.asarray(max_bounds, np.float64)
@@ -361,6 +367,9 @@ class SortLastSession:
         """Merge the partial images of all ranks.  Returns ``((lo, hi), piece)``: this rank's fully composited
         pixel range (a float32 ``(hi-lo, 4)`` tensor, or for ``"p2p"`` the device pointer of that range)."""
         cam = camera_in_voxels(camera_pos, self.min_bounds, self.max_bounds, self.shape)
+        if self._bound is None and self._over is None:
+            # the march that filled the image ran on a stream this session does not know: wait for the device
+            self.torch.cuda.synchronize()
         if self.exchange == "p2p":
             return self._composite_p2p(cam)
         torch, dist = self.torch, self.dist
@@ -427,6 +436,8 @@ class SortLastSession:
             _cabi.finalize_rgba8(self.device, piece, self._dst_frame_ptr(dst) + lo * 4, n, flags,
                                  torch.cuda.current_stream().cuda_stream)
             self._fence()
+            if self._bound is None:       # the next march may run on another stream: it must not overwrite the image
+                torch.cuda.current_stream().synchronize()   # while a peer's merge or this finalize still reads it
             return self._frame.ptr if self.rank == dst else None
         per = -(-self.n_pixels // self.world)            # pieces differ by at most one pixel: pad to the largest
         if self._gather_out is None:
@@ -438,6 +449,8 @@ class SortLastSession:
         _cabi.finalize_rgba8(self.device, ptr, out.data_ptr(), n, flags, torch.cuda.current_stream().cuda_stream)
         gathered = self._gather_in
         dist.gather(out, gathered, dst=dst, group=self.group)
+        if self._bound is None and self._over is None:
+            torch.cuda.current_stream().synchronize()
         if self.rank != dst:
             return None
         frame = self._gather_frame
@@ -457,6 +470,18 @@ class SortLastSession:
             if buf is not None:
                 buf.close()
         self._own = self._frame = None
+
+
+def _bind_stream(session, renderer):
+    """Stream discipline of the executors: merges, finalize, NCCL traffic and fences are enqueued on torch's
+    CURRENT stream, so the renderer must march on that stream too -- otherwise the next frame's march could
+    overwrite the partial image while this rank's finalize, or a peer's merge across NVLink, still reads the
+    previous one.  ``pyvr_cuda_set_stream`` orders the renderer's pending work before the new stream.  A session
+    that was never bound falls back to host synchronisation around every frame."""
+    stream = session.torch.cuda.current_stream().cuda_stream
+    if session._bound != (id(renderer), stream):
+        renderer.set_stream(stream)
+        session._bound = (id(renderer), stream)
 
 
 def reduce_tile_frames(frame, dst: int = 0, group=None):

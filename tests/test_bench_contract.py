@@ -22,9 +22,20 @@ def test_reference_arm_prints_the_contract_line():
     assert line["n_gpus"] == 1 and line["steps"] == 1 and line["warmup"] == 0 and line["value"] > 0
     assert line["vs_baseline"] is None and line["data"] == "synthetic" and "workload" in line["config"]
     cb = line["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and "views" in cb["sample"]
+    # "reference" = the reference's GLSL on Mesa llvmpipe (oracle/gl); "port" = the C restatement when Mesa is missing
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == line["value"] and "view" in cb["sample"]
     assert line["e2e"] == {"value": line["value"], "unit": "Gsamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert line["gpu_launches"] == 0
+
+
+def test_reference_arm_uses_all_host_threads_under_torchrun():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm must not inherit that (round-1 SCALE runs did)."""
+    out = _run("--impl", "reference", "--size", "32", "--width", "64", "--height", "48", "--steps", "1", "--warmup", "0",
+               "--reference-backend", "oracle", env={"OMP_NUM_THREADS": "1", "RANK": "0", "WORLD_SIZE": "2", "LOCAL_RANK": "0"})
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    cores = len(os.sched_getaffinity(0))
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] == cores
 
 
 def test_reference_arm_other_ranks_exit_quietly():
