@@ -195,8 +195,16 @@ def use_all_host_threads():
 # --------------------------------------------------------------------------------------------------
 # CPU arm: the reference's shader on Mesa llvmpipe (oracle/gl), else the C/OpenMP restatement (oracle/)
 # --------------------------------------------------------------------------------------------------
+LLVMPIPE_CHECK_SIZE = 384   # largest multiple of 128 whose RGB32F normal texture fits Mesa 18 llvmpipe's 1 GiB cap (406^3)
+
+
 class CpuReference:
-    """C3 scene loaded once into the CPU renderer; ``render_view(k)`` = one whole 1920x1080 turntable view."""
+    """C3 scene loaded once into the CPU renderer; ``render_view(k)`` = one whole turntable view.
+
+    Preferred: the reference's own GLSL on Mesa llvmpipe (``oracle/gl``, ``kind = "reference"``).  The Mesa 18.1.9
+    build in this image caps a texture at 1 GiB and stores RGB32F as RGBA32F, so the 512^3 normal texture of C3
+    (2 GiB) cannot be created: at that size the arm falls back to the C/OpenMP restatement (``kind = "port"``) and
+    ``llvmpipe_check()`` times both CPU renderers on the same scene at 384^3 to show how they compare."""
 
     def __init__(self, args, data, normals, light, config, lut, backend="auto"):
         import oracle
@@ -207,27 +215,40 @@ class CpuReference:
                           max_bounds=np.array([1, 1, 1], np.float32))
         self.oracle, self.gl, self.kind = oracle, None, "port"
         self.cores = oracle.num_threads()
-        self.what = ("CPU restatement of the reference shader (oracle/pyvr_oracle.c, C + OpenMP); Mesa llvmpipe "
-                     "not available on this box")
+        self.what = "CPU restatement of the reference shader (oracle/pyvr_oracle.c, C + OpenMP)"
+        self.gl_error = None
         if backend in ("auto", "gl"):
             try:
-                import oracle.gl as ogl
-
-                r = ogl.GLReference(args.width, args.height)
-                r.load_shaders()
-                r.set_config(config.step_size, config.max_steps, config.reference_step_size)
-                r.set_light(light.ambient_intensity, light.diffuse_intensity, light.position, light.target)
-                r.load_volume(self.vol.data, self.vol.normals, self.vol.min_bounds, self.vol.max_bounds)
-                r.set_lut(lut)
-                self.gl, self.kind = r, "reference"
+                self.gl = self._gl_renderer(self.vol)
+                self.kind = "reference"
                 self.cores = int(os.environ.get("LP_NUM_THREADS", min(host_threads(), 16)))
-                self.what = ("the reference's own GLSL (pyvr/shaders/volume.frag.glsl, verbatim) on " + r.info["renderer"]
-                             + ", " + r.info["version"] + ", driven as pyvr/moderngl_renderer/manager.py drives it "
+                self.what = ("the reference's own GLSL (pyvr/shaders/volume.frag.glsl, verbatim) on " + self.gl.info["renderer"]
+                             + ", " + self.gl.info["version"] + ", driven as pyvr/moderngl_renderer/manager.py drives it "
                              "(oracle/gl: ctypes OpenGL, moderngl is not in the image); clear + draw + glReadPixels per view")
-            except Exception as e:   # GLUnavailable, compile errors, ...
+            except Exception as e:   # GLUnavailable (no Mesa, texture too large), compile errors, ...
                 if backend == "gl":
                     raise
-                self.what += f" ({type(e).__name__}: {e})"
+                self.gl_error = f"{type(e).__name__}: {e}"
+                self.what += "; the reference's GLSL on Mesa llvmpipe could not take this scene: " + self.gl_error
+
+    def _gl_renderer(self, vol):
+        import oracle.gl as ogl
+
+        r = ogl.GLReference(self.args.width, self.args.height)
+        r.load_shaders()
+        r.set_config(self.config.step_size, self.config.max_steps, self.config.reference_step_size)
+        r.set_light(self.light.ambient_intensity, self.light.diffuse_intensity, self.light.position, self.light.target)
+        r.load_volume(vol.data, vol.normals, vol.min_bounds, vol.max_bounds)
+        r.set_lut(self.lut)
+        return r
+
+    def _gl_view(self, gl, k):
+        cam = turntable_camera(k)
+        pos, _ = cam.get_camera_vectors()
+        gl.set_camera(cam.get_view_matrix(), cam.get_projection_matrix(self.args.width / self.args.height), pos)
+        t0 = time.perf_counter()
+        gl.render()
+        return time.perf_counter() - t0
 
     def samples_of(self, k):
         """Reference samples of view k (the unit of the metric): counted by the restatement, which executes the
@@ -238,15 +259,38 @@ class CpuReference:
 
     def render_view(self, k):
         """Returns (seconds, samples or None).  With GL the sample count comes from ``samples_of`` (untimed)."""
+        if self.gl is not None:
+            return self._gl_view(self.gl, k), None
         cam = turntable_camera(k)
         t0 = time.perf_counter()
-        if self.gl is not None:
-            pos, _ = cam.get_camera_vectors()
-            self.gl.set_camera(cam.get_view_matrix(), cam.get_projection_matrix(self.args.width / self.args.height), pos)
-            self.gl.render()
-            return time.perf_counter() - t0, None
         _, _, st = self.oracle.render(self.vol, cam, self.light, self.config, self.lut, self.args.width, self.args.height)
         return time.perf_counter() - t0, st["samples"]
+
+    def llvmpipe_check(self, k=0):
+        """The reference's GLSL on llvmpipe next to the C restatement on the SAME scene at 384^3 (the largest
+        volume this llvmpipe can hold), one whole view each after a warm-up view."""
+        from pyvr_b200 import Volume, create_sample_volume
+
+        try:
+            data = create_sample_volume(LLVMPIPE_CHECK_SIZE, "double_sphere")
+            vol = Volume(data=data, normals=self.oracle.normals(data), min_bounds=self.vol.min_bounds, max_bounds=self.vol.max_bounds)
+            gl = self._gl_renderer(vol)
+            self._gl_view(gl, k)
+            t_gl = self._gl_view(gl, k)
+            info = gl.info
+            gl.close()
+            cam = turntable_camera(k)
+            t0 = time.perf_counter()
+            _, _, st = self.oracle.render(vol, cam, self.light, self.config, self.lut, self.args.width, self.args.height)
+            t_port = time.perf_counter() - t0
+            return {"scene": f"C3 with a {LLVMPIPE_CHECK_SIZE}^3 volume, {self.args.width}x{self.args.height}, turntable view {k}",
+                    "samples": st["samples"], "llvmpipe_Gsamples_per_s": st["samples"] / t_gl / 1e9, "llvmpipe_seconds": t_gl,
+                    "llvmpipe_threads": int(os.environ.get("LP_NUM_THREADS", min(host_threads(), 16))),
+                    "port_Gsamples_per_s": st["samples"] / t_port / 1e9, "port_seconds": t_port,
+                    "port_threads": self.oracle.num_threads(), "port_over_llvmpipe": t_gl / t_port,
+                    "gl": info["renderer"] + ", " + info["version"]}
+        except Exception as e:
+            return {"error": f"{type(e).__name__}: {e}"}
 
 
 def cpu_baseline(ref, view_indices, target_seconds):
@@ -260,12 +304,15 @@ def cpu_baseline(ref, view_indices, target_seconds):
         views += 1
         if dt >= target_seconds:
             break
-    return {
+    out = {
         "value": samples / dt / 1e9, "unit": "Gsamples/s", "cores": ref.cores, "kind": ref.kind,
         "sample": f"{views} whole views of the step (turntable views {view_indices[0]}..{view_indices[views - 1]}, "
                   f"{samples} samples) in {dt:.2f} s after one warm-up view; {ref.what}",
         "seconds": dt, "frames_per_s": views / dt,
     }
+    if ref.kind == "port":
+        out["llvmpipe_check"] = ref.llvmpipe_check(view_indices[0])
+    return out
 
 
 def run_reference(args, rank):
@@ -302,7 +349,7 @@ def run_reference(args, rank):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args),
         "cpu_baseline": {"value": value, "unit": "Gsamples/s", "cores": ref.cores, "kind": ref.kind, "sample": sample,
-                         "host_cores": cores},
+                         "host_cores": cores, **({"llvmpipe_check": ref.llvmpipe_check(ks[args.warmup])} if ref.kind == "port" else {})},
         "e2e": {"value": value, "unit": "Gsamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -642,9 +689,12 @@ def main():
             line.update(secondary)
     elif rank == 0 and not args.skip_cpu_baseline and world == 1:
         cores = use_all_host_threads()
-        ref = CpuReference(args, data, normals, light, config, lut, args.reference_backend)
-        line["cpu_baseline"] = cpu_baseline(ref, step_view_indices(args.warmup, 0, 1, per_step), args.cpu_seconds)
-        line["cpu_baseline"]["host_cores"] = cores
+        try:
+            ref = CpuReference(args, data, normals, light, config, lut, args.reference_backend)
+            line["cpu_baseline"] = cpu_baseline(ref, step_view_indices(args.warmup, 0, 1, per_step), args.cpu_seconds)
+            line["cpu_baseline"]["host_cores"] = cores
+        except Exception as e:      # the GPU numbers above must not be lost to a failure of the CPU arm
+            line["cpu_baseline"] = {"error": f"{type(e).__name__}: {e}"}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

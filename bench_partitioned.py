@@ -106,8 +106,7 @@ def measure(args, rank, world, local_rank, workload, steps, warmup, size=None, w
         brick, session = None, None
         gen_ms = renderer.generate_volume(args.size, "double_sphere", bmin, bmax)
         stored = shape
-        if world > 1:
-            renderer.set_pixel_shard(rank, world)
+    tiles = mg.TileSession(renderer, n_pixels, device=local_rank) if (not c5 and world > 1) else None
     renderer.set_lut(lut)
     renderer.set_camera(camera)
     setup_s = time.perf_counter() - t0
@@ -143,18 +142,23 @@ def measure(args, rank, world, local_rank, workload, steps, warmup, size=None, w
         if session is not None:
             renderer.render_accum_to_device(session.image_ptr())
             st = renderer.stats
-            piece_range, piece = session.composite(position)
+            piece_range, piece = session.composite(position, finalize_to=0 if args.exchange == "p2p" else None)
             out = session.gather_rgba8(piece_range, piece)
             if out is not None:
                 frame_ptr = out if isinstance(out, int) else out.data_ptr()
+        elif tiles is not None:
+            out = tiles.render()                 # march + peer stores into rank 0's frame + two flags
+            st = renderer.stats
+            if out is not None:
+                frame_ptr = out
         else:
             renderer.render_to_device(frame.data_ptr())
             st = renderer.stats
-            if world > 1:
-                mg.reduce_tile_frames(frame, dst=0)
         if read_back and rank == 0:
             _cabi.check(_cabi.lib().pyvr_cuda_memcpy(local_rank, pinned.array.ctypes.data, ctypes.c_void_p(frame_ptr),
                                                      n_pixels * 4, 2, ctypes.c_void_p(stream.cuda_stream)))
+        if tiles is not None:
+            tiles.release()
         return st
 
     for _ in range(args.warmup):
@@ -175,6 +179,7 @@ def measure(args, rank, world, local_rank, workload, steps, warmup, size=None, w
     ms = reduce_max(e0.elapsed_time(e1))
     all_samples, all_fetched = reduce_sum(float(samples)), reduce_sum(float(fetched))
     march_ms = reduce_max(kernel_ms)
+    march_ms_mean = reduce_sum(kernel_ms) / world
 
     for _ in range(args.warmup):
         step(read_back=True)
@@ -200,7 +205,8 @@ def measure(args, rank, world, local_rank, workload, steps, warmup, size=None, w
                 f"of {stored[0]}x{stored[1]}x{stored[2]} (+1 ghost), {width}x{height}, high_quality, binary swap ({args.exchange}) "
                 "over NVLink, isometric view" if c5 else
                 f"C4: synthetic {args.size}^3 f16 scalar+normal double_sphere generated on device and replicated, {width}x{height}, "
-                f"ultra_quality, ESS, isometric view, 64x64 tile groups round-robin over {world} GPU(s), reduce(SUM) of uint8 frames")
+                f"ultra_quality, ESS, isometric view, 32x16-pixel tile groups dealt over {world} GPU(s), pixels stored straight into "
+                "rank 0's frame over NVLink by the march kernel (no reduce / gather pass)")
         line = {
             "metric": "ray-march throughput", "value": all_samples / (ms * 1e-3) / 1e9, "unit": "Gsamples/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
@@ -223,6 +229,8 @@ def measure(args, rank, world, local_rank, workload, steps, warmup, size=None, w
                          "march_share_of_step": march_ms / ms,
                          "l1": {"achieved": achieved, "peak": l1_peak, "unit": "GB/s", "frac": achieved / l1_peak},
                          "note": "per-GPU figures of the slowest rank's march; exchange/merge/gather are the rest of the step"},
+            "balance": {"march_ms_slowest_rank": march_ms / args.steps, "march_ms_mean_over_ranks": march_ms_mean / args.steps,
+                        "imbalance": march_ms / march_ms_mean if march_ms_mean > 0 else None},
             "clocks": clocks.summary(),
             "volume_generation": {"ms": gen_ms, "voxels_per_gpu": voxels, "Gvoxels/s": voxels / (gen_ms * 1e-3) / 1e9},
             "setup_s": setup_s,
@@ -232,6 +240,8 @@ def measure(args, rank, world, local_rank, workload, steps, warmup, size=None, w
 
     if session is not None:
         session.close()
+    if tiles is not None:
+        tiles.close()
     renderer.close()
     pinned.close()
     del frame
@@ -283,14 +293,22 @@ def parity_check(rank, world, local_rank):
         r.set_lut(lut)
         want = np.frombuffer(r.render(), np.uint8).reshape(H, W, 4).copy()
         want_samples = r.stats["samples"]
-        # (1) image tiles
+        # (1) image tiles: cleared frames + reduce(SUM), and the fused path (peer stores into rank 0's frame)
         r.set_pixel_shard(rank, world)
         tiles = torch.zeros(H * W * 4, dtype=torch.uint8, device="cuda")
         r.render_to_device(tiles.data_ptr())
         mg.reduce_tile_frames(tiles, dst=0)
         r.set_pixel_shard(0, 1)
+        ts = mg.TileSession(r, W * H, device=local_rank)
+        for _ in range(2):
+            ptr = ts.render()
+            if ptr is not None:
+                fused = frame_of(ptr).copy()
+            ts.release()
+        ts.close()
         if rank == 0:
             out["tiles_bit_identical"] = bool(np.array_equal(frame_of(tiles), want))
+            out["tiles_fused_bit_identical"] = bool(np.array_equal(fused, want))
         # (2) sort-last bricks, both exchange paths; (3) relay
         if world & (world - 1) == 0:
             b = mg.brick_of_rank(data.shape, rank, world)
@@ -300,9 +318,9 @@ def parity_check(rank, world, local_rank):
             r.set_lut(lut)
             for exchange in ("p2p", "nccl"):
                 session = mg.SortLastSession(data.shape, vol.min_bounds, vol.max_bounds, W * H, device=local_rank, exchange=exchange, renderer=r)
-                for _ in range(2):                   # twice: buffers are reused across frames
+                for it in range(3):                  # several frames: buffers and flags are reused; the last one fused
                     r.render_accum_to_device(session.image_ptr())
-                    piece_range, piece = session.composite(position)
+                    piece_range, piece = session.composite(position, finalize_to=0 if (exchange == "p2p" and it == 2) else None)
                     frame = session.gather_rgba8(piece_range, piece)
                 samples = torch.tensor([r.stats["samples"]], dtype=torch.int64, device="cuda")
                 dist.all_reduce(samples)
@@ -332,7 +350,7 @@ def parity_check(rank, world, local_rank):
                                        "psnr_db": float("inf") if mse == 0 else float(10 * np.log10(255.0 ** 2 / mse))}
     except Exception as e:
         out["single_gpu_vs_oracle"] = {"error": f"{type(e).__name__}: {e}"}
-    checks = [out.get("tiles_bit_identical", False)]
+    checks = [out.get("tiles_bit_identical", False), out.get("tiles_fused_bit_identical", False)]
     if world & (world - 1) == 0:
         checks += [out["sort_last_p2p"]["ok"], out["sort_last_nccl"]["ok"], out["relay_bit_identical"]]
     out["all_ok"] = bool(all(checks))

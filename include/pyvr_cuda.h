@@ -145,9 +145,12 @@ int pyvr_cuda_generate_volume(pyvr_ctx *ctx, int shape, int size, const int loca
  * stored block; either may be NULL). */
 int pyvr_cuda_read_texels(pyvr_ctx *ctx, float *scalar, float *normals);
 
-/* Image-space sharding (SURVEY.md section 8 e, config C4): this context marches the 64x64-pixel tile
- * groups g with g % count == rank and writes zeros elsewhere, so the frames of all ranks add up
- * (e.g. ncclReduce SUM over uint8) to the full frame, bit for bit.  count = 1 restores normal rendering. */
+/* Image-space sharding (SURVEY.md section 8 e, config C4): this context marches only its own tile groups --
+ * groups of 2^s x 2^s CTA tiles of 16x8 pixels (option "shard_shift", default s = 1), owner(gx, gy) =
+ * (gx + gy) mod count -- and only those CTAs are launched.  By default the rest of the frame is cleared first, so
+ * the frames of all ranks add up (e.g. ncclReduce SUM over uint8) to the full frame, bit for bit; with option
+ * "shard_in_place" = 1 the other pixels are left untouched, so that all ranks can write one shared (peer-mapped)
+ * frame directly.  count = 1 restores normal rendering. */
 int pyvr_cuda_set_pixel_shard(pyvr_ctx *ctx, int rank, int count);
 
 /* --- create_rgba_transfer_function_texture (manager.py:137-186): (size,4) RGBA binary32 ---------- */
@@ -200,6 +203,16 @@ int pyvr_cuda_composite_over(int device, const float *front, const float *back, 
 /* Blend onto the cleared target + RGBA8 quantisation of a composited image (manager.py:217-220, 29). */
 int pyvr_cuda_finalize_rgba8(int device, const float *accum, uint8_t *out, size_t n_pixels, uint32_t flags,
                              void *cuda_stream);
+/* Last round of a binary swap fused with finalize: out = rgba8(front over back) for n_pixels; accum_out (may be
+ * NULL, may alias front) also receives the merged floats.  out may be a peer-mapped frame. */
+int pyvr_cuda_composite_finalize(int device, const float *front, const float *back, float *accum_out, uint8_t *out,
+                                 size_t n_pixels, float termination_alpha, uint32_t flags, void *cuda_stream);
+/* Stream-ordered flags between the GPUs of a node (uint32 counters in pyvr_cuda_device_alloc / peer-mapped memory).
+ * signal: everything enqueued on the stream before is visible system-wide, then *flag = value (release, system
+ * scope).  wait: the stream stalls until every one of flags[0..n_flags) has reached `value` (counters only grow;
+ * comparison is wrap-safe).  They replace host barriers / NCCL fences around peer reads and writes. */
+int pyvr_cuda_flag_signal(int device, uint32_t *flag, uint32_t value, void *cuda_stream);
+int pyvr_cuda_flag_wait(int device, const uint32_t *flags, int n_flags, uint32_t value, void *cuda_stream);
 /* Plain cudaMalloc memory (IPC-exportable, unlike a sub-allocation of a framework's caching pool). */
 int pyvr_cuda_device_alloc(int device, size_t bytes, void **out);
 int pyvr_cuda_device_free(int device, void *ptr);
@@ -212,8 +225,9 @@ int pyvr_cuda_memcpy(int device, void *dst, const void *src, size_t bytes, int k
 int pyvr_cuda_stream_synchronize(int device, void *cuda_stream);
 
 /* --- misc ------------------------------------------------------------------------------------------ */
-/* Tuning knobs (no reference counterpart).  "swizzle": 1 (default) = L1 bank swizzle of the packed texel
- * layout, 0 = plain rows (for A/B profiling); must be set before pyvr_cuda_upload_volume. */
+/* Tuning knobs (no reference counterpart).  "swizzle": 1 (default) = bank-rotating row/plane padding of the packed
+ * texel layout, 0 = aligned rows (for A/B profiling); must be set before pyvr_cuda_upload_volume.  "pair": z-pair
+ * entries (-1 auto, 0 off, 1 on; next upload).  "shard_shift", "shard_in_place": see pyvr_cuda_set_pixel_shard. */
 int pyvr_cuda_set_option(pyvr_ctx *ctx, const char *key, int value);
 /* Roofline denominators measured on the spot (no reference counterpart; csrc/bandwidth.cu): bytes per second
  * delivered to registers by coalesced 128-bit loads that hit L1 (level 1: the SM load-return path that bounds

@@ -235,6 +235,12 @@ class GLReference:
         par(GL_TEXTURE_3D, GL_TEXTURE_WRAP_S, GL_CLAMP_TO_EDGE)
         par(GL_TEXTURE_3D, GL_TEXTURE_WRAP_T, GL_CLAMP_TO_EDGE)
         par(GL_TEXTURE_3D, GL_TEXTURE_WRAP_R, GL_CLAMP_TO_EDGE)
+        err = g.fn("glGetError", c_uint)()
+        if err:   # Mesa 18 llvmpipe caps one texture at 1 GiB and stores RGB32F as RGBA32F: normals stop at 406^3
+            nbytes = int(shape[0]) * int(shape[1]) * int(shape[2]) * (16 if components == 3 else 4)
+            raise GLUnavailable(f"glTexImage3D {tuple(int(v) for v in shape)} x {components} float failed with 0x{err:x}"
+                                f"{' (GL_OUT_OF_MEMORY)' if err == 0x505 else ''}: {nbytes / 2 ** 30:.2f} GiB exceeds this "
+                                "llvmpipe's 1 GiB-per-texture limit")
         self._textures.append(tex.value)
         return tex.value
 

@@ -70,6 +70,8 @@ struct pyvr_ctx {
     size_t n_cells = 0;
     bool swizzle = true;  // L1 bank swizzle of the texel layout (common.cuh); off only for A/B profiling
     int shard_rank = 0, shard_count = 1;   // image-space tile sharding (pyvr_cuda_set_pixel_shard)
+    int shard_shift = 1;                   // tile groups of 2^shift x 2^shift CTA tiles (32x16 pixels by default)
+    bool shard_in_place = false;           // true: foreign pixels are left untouched (all ranks write one shared frame)
     int pair_option = -1;   // z-pair entries: -1 auto (when the doubled array stays under kPairBudget), 0 off, 1 on
     bool use_pair = false;  // decided per upload
     cudaArray_t tex_array = nullptr;        // PYVR_FLAG_HWTEX: built on first use from the packed texels
@@ -327,6 +329,7 @@ MarchArgs make_args(const pyvr_ctx *c) {
     a.counters = c->d_counters;
     a.shard_rank = c->shard_rank;
     a.shard_count = c->shard_count;
+    a.shard_shift = c->shard_shift;
     return a;
 }
 
@@ -343,6 +346,13 @@ int march(pyvr_ctx *c, int first, int n, uchar4 *out8, float4 *out_acc, size_t e
     a.out8 = out8;
     a.out_acc = out_acc;
     a.in_acc = in_acc;
+    if (c->shard_count > 1) {
+        if (in_acc) return fail(PYVR_ERR_STATE, "relay rendering cannot be combined with image-space sharding");
+        if (!c->shard_in_place) {   // the launch covers this rank's tiles only: everything else reads as cleared
+            if (out8) CU(cudaMemsetAsync(out8, 0, frame_pixels(c) * sizeof(uchar4) * (size_t)n, c->stream));
+            if (out_acc) CU(cudaMemsetAsync(out_acc, 0, frame_pixels(c) * sizeof(float4) * (size_t)n, c->stream));
+        }
+    }
     CU(cudaEventRecord(c->ev[2 * ev_pair], c->stream));
     CU(launch_march(a, n, c->half_texels, c->texel_bytes / entry_bytes(c->half_texels, c->vol.pair) >= ((size_t)1 << 31), c->stream));
     CU(cudaEventRecord(c->ev[2 * ev_pair + 1], c->stream));
@@ -472,6 +482,15 @@ int pyvr_cuda_set_option(pyvr_ctx *c, const char *key, int value) {
     if (!c || !key) return fail(PYVR_ERR_INVALID, "ctx or key is NULL");
     if (strcmp(key, "pair") == 0) {   // takes effect at the next upload
         c->pair_option = value < 0 ? -1 : (value != 0);
+        return PYVR_OK;
+    }
+    if (strcmp(key, "shard_shift") == 0) {      // tile-group edge of the image-space sharding, in CTA tiles (log2)
+        if (value < 0 || value > 6) return fail(PYVR_ERR_INVALID, "shard_shift must be in [0, 6]");
+        c->shard_shift = value;
+        return PYVR_OK;
+    }
+    if (strcmp(key, "shard_in_place") == 0) {   // 1: a sharded render leaves the other ranks' pixels untouched
+        c->shard_in_place = value != 0;
         return PYVR_OK;
     }
     if (strcmp(key, "swizzle") == 0) {
@@ -961,6 +980,31 @@ int pyvr_cuda_finalize_rgba8(int device, const float *accum, uint8_t *out, size_
     DeviceGuard guard(device);
     CU(launch_finalize_rgba8(reinterpret_cast<const float4 *>(accum), reinterpret_cast<uchar4 *>(out), n_pixels,
                              flags, (cudaStream_t)cuda_stream));
+    return PYVR_OK;
+}
+
+int pyvr_cuda_composite_finalize(int device, const float *front, const float *back, float *accum_out, uint8_t *out,
+                                 size_t n_pixels, float termination_alpha, uint32_t flags, void *cuda_stream) {
+    if (!front || !back || !out) return fail(PYVR_ERR_INVALID, "NULL argument");
+    DeviceGuard guard(device);
+    CU(launch_composite_finalize(reinterpret_cast<const float4 *>(front), reinterpret_cast<const float4 *>(back),
+                                 reinterpret_cast<float4 *>(accum_out), reinterpret_cast<uchar4 *>(out), n_pixels,
+                                 termination_alpha, flags, (cudaStream_t)cuda_stream));
+    return PYVR_OK;
+}
+
+int pyvr_cuda_flag_signal(int device, uint32_t *flag, uint32_t value, void *cuda_stream) {
+    if (!flag) return fail(PYVR_ERR_INVALID, "flag is NULL");
+    DeviceGuard guard(device);
+    CU(launch_flag_signal(flag, value, (cudaStream_t)cuda_stream));
+    return PYVR_OK;
+}
+
+int pyvr_cuda_flag_wait(int device, const uint32_t *flags, int n_flags, uint32_t value, void *cuda_stream) {
+    if (!flags) return fail(PYVR_ERR_INVALID, "flags is NULL");
+    if (n_flags < 1 || n_flags > 1024) return fail(PYVR_ERR_INVALID, "n_flags must be in [1, 1024]");
+    DeviceGuard guard(device);
+    CU(launch_flag_wait(flags, n_flags, value, (cudaStream_t)cuda_stream));
     return PYVR_OK;
 }
 

@@ -86,10 +86,11 @@ struct MarchArgs {
     const float4 *in_acc;          // relay (sort-last, exact): fragment colour accumulated by the bricks in
                                    // front of this one; the march continues from it.  May be null / == out_acc.
     unsigned long long *counters;  // [samples, fetched, rays_hit, rays_terminated]
-    // Image-space sharding (multi-GPU tiles): 64x64-pixel tile groups are dealt round-robin; this launch
-    // marches the groups with (group index) % shard_count == shard_rank and writes zeros elsewhere, so the
-    // per-rank frames add up to the full frame.  shard_count <= 1: everything.
-    int shard_rank, shard_count;
+    // Image-space sharding (multi-GPU tiles): groups of 2^shard_shift x 2^shard_shift CTA tiles (16x8 pixels each)
+    // are dealt over the ranks, owner(gx, gy) = (gx + gy) mod shard_count; this launch marches the groups of
+    // shard_rank only and leaves every other pixel untouched (the C ABI clears the frame first unless the caller
+    // asked for in-place sharding into a frame that all ranks write).  shard_count <= 1: everything.
+    int shard_rank, shard_count, shard_shift;
 };
 
 // Fragment colour -> what fbo.read returns: clamp to [0,1], blend SRC_ALPHA / ONE_MINUS_SRC_ALPHA onto the
@@ -119,6 +120,12 @@ cudaError_t launch_composite_over(const float4 *front, const float4 *back, float
                                   float term_alpha, cudaStream_t stream);
 cudaError_t launch_finalize_rgba8(const float4 *accum, uchar4 *out, size_t n_pixels, unsigned flags,
                                   cudaStream_t stream);
+// last binary-swap round fused with finalize: out8 = rgba8(front over back); accum_out (may be null) keeps the floats
+cudaError_t launch_composite_finalize(const float4 *front, const float4 *back, float4 *accum_out, uchar4 *out8,
+                                      size_t n_pixels, float term_alpha, unsigned flags, cudaStream_t stream);
+// stream-ordered flags in (peer) device memory: signal = system-scope release store, wait = spin until *flag >= value
+cudaError_t launch_flag_signal(unsigned *flag, unsigned value, cudaStream_t stream);
+cudaError_t launch_flag_wait(const unsigned *flags, int n_flags, unsigned value, cudaStream_t stream);
 cudaError_t launch_pack_texels(const float *scalar, const float *normals, const VolumeDesc &vol,
                                bool half_texels, cudaStream_t stream);
 // replicate the edge texels of the stored block into the one-texel apron (after every pack / generate)

@@ -26,23 +26,58 @@
 namespace pyvr {
 namespace {
 
+// `over` of one pixel (shared by the plain and the fused kernels)
+__device__ __forceinline__ float4 over_pixel(float4 f, const float4 *back, size_t p, float term_alpha) {
+    if (f.w < term_alpha) {
+        const float4 b = __ldcs(back + p);
+        float t = 1.0f - f.w;
+        if (fmaf(t, b.w, f.w) > term_alpha) t = (term_alpha - f.w) / b.w;
+        f.x = fmaf(t, b.x, f.x);
+        f.y = fmaf(t, b.y, f.y);
+        f.z = fmaf(t, b.z, f.z);
+        f.w = fmaf(t, b.w, f.w);
+    }
+    return f;
+}
+
 __global__ void __launch_bounds__(256)
 composite_over_kernel(const float4 *__restrict__ front, const float4 *__restrict__ back,
                       float4 *__restrict__ out, size_t n, float term_alpha) {
     for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (size_t)gridDim.x * blockDim.x) {
-        float4 f = front[p];
-        if (f.w < term_alpha) {
-            // streaming load: a peer buffer is read exactly once
-            const float4 b = __ldcs(back + p);
-            float t = 1.0f - f.w;
-            if (fmaf(t, b.w, f.w) > term_alpha) t = (term_alpha - f.w) / b.w;   // s * (1 - f.w), s < 1; b.w > 0 here
-            f.x = fmaf(t, b.x, f.x);
-            f.y = fmaf(t, b.y, f.y);
-            f.z = fmaf(t, b.z, f.z);
-            f.w = fmaf(t, b.w, f.w);
-        }
+        const float4 f = over_pixel(front[p], back, p, term_alpha);   // streaming load of `back`: a peer buffer is read once
         out[p] = f;
     }
+}
+
+// Last round of the binary swap fused with the blend + RGBA8 quantisation: the merged floats never travel
+// through memory again (out8 may be a peer-mapped frame: 4 bytes per pixel cross NVLink instead of a later gather).
+__global__ void __launch_bounds__(256)
+composite_finalize_kernel(const float4 *__restrict__ front, const float4 *__restrict__ back, float4 *accum_out,
+                          uchar4 *__restrict__ out8, size_t n, float term_alpha, unsigned flags, int front_is_streamed) {
+    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (size_t)gridDim.x * blockDim.x) {
+        const float4 f = over_pixel(front_is_streamed ? __ldcs(front + p) : front[p], back, p, term_alpha);
+        if (accum_out) accum_out[p] = f;
+        out8[p] = fragment_to_rgba8(f.x, f.y, f.z, f.w, flags);
+    }
+}
+
+// Stream-ordered flags between GPUs.  signal: everything this stream did before (kernels that wrote peer memory)
+// is made visible system-wide, then the flag is stored with release semantics at system scope.  wait: one thread
+// per flag spins with an acquire load until it reaches `value` (monotonic counters: frame number * stages + stage).
+__global__ void flag_signal_kernel(unsigned *flag, unsigned value) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(value) : "memory");
+}
+
+__global__ void flag_wait_kernel(const unsigned *flags, int n_flags, unsigned value) {
+    if ((int)threadIdx.x < n_flags) {
+        unsigned v;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + threadIdx.x) : "memory");
+            if ((int)(v - value) < 0) __nanosleep(200);
+        } while ((int)(v - value) < 0);
+    }
+    __threadfence_system();
 }
 
 __global__ void __launch_bounds__(256)
@@ -64,6 +99,24 @@ inline int stream_grid(size_t n) {
 cudaError_t launch_composite_over(const float4 *front, const float4 *back, float4 *out, size_t n_pixels,
                                   float term_alpha, cudaStream_t stream) {
     composite_over_kernel<<<stream_grid(n_pixels), 256, 0, stream>>>(front, back, out, n_pixels, term_alpha);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_composite_finalize(const float4 *front, const float4 *back, float4 *accum_out, uchar4 *out8,
+                                      size_t n_pixels, float term_alpha, unsigned flags, cudaStream_t stream) {
+    composite_finalize_kernel<<<stream_grid(n_pixels), 256, 0, stream>>>(front, back, accum_out, out8, n_pixels, term_alpha,
+                                                                         flags, 0);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_flag_signal(unsigned *flag, unsigned value, cudaStream_t stream) {
+    flag_signal_kernel<<<1, 1, 0, stream>>>(flag, value);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_flag_wait(const unsigned *flags, int n_flags, unsigned value, cudaStream_t stream) {
+    if (n_flags < 1 || n_flags > 1024) return cudaErrorInvalidValue;
+    flag_wait_kernel<<<1, ((n_flags + 31) / 32) * 32, 0, stream>>>(flags, n_flags, value);
     return cudaGetLastError();
 }
 

@@ -173,15 +173,36 @@ struct Accum {
     float r, g, b, a;
 };
 
-// The transfer-function LUT in shared memory, pair-packed like the z-pair texels: entry j (0 <= j <= size) holds
-// {lut[max(j-1, 0)], lut[min(j, size-1)]}, i.e. both taps of a fetch whose lower tap floor(x) is j - 1.  A fetch is
-// one clamp of floor(x) to [-1, size-1] and two LDS.128 at one address; out-of-range densities land on an entry
-// whose halves are equal (CLAMP_TO_EDGE).
+// The transfer-function LUT in shared memory.  PYVR_LUT_PAIRED (default): pair-packed like the z-pair texels --
+// entry j (0 <= j <= size) holds {lut[max(j-1, 0)], lut[min(j, size-1)]}, i.e. both taps of a fetch whose lower tap
+// floor(x) is j - 1; a fetch is one clamp of floor(x) to [-1, size-1] and two LDS.128 at one address, and
+// out-of-range densities land on an entry whose halves are equal (CLAMP_TO_EDGE).  Unpaired: entry j = lut[j - 1]
+// with one apron entry on each side (same clamp, taps 16 bytes apart).
+#ifndef PYVR_LUT_PAIRED
+#define PYVR_LUT_PAIRED 1
+#endif
+__host__ __device__ constexpr size_t lut_smem_bytes(int size) {
+    return PYVR_LUT_PAIRED ? ((size_t)size + 1) * 2 * sizeof(float4) : ((size_t)size + 2) * sizeof(float4);
+}
 __device__ __forceinline__ void stage_lut(float4 *s_lut, const float4 *lut, int size, int n_threads) {
+#if PYVR_LUT_PAIRED
     for (int j = threadIdx.x; j <= size; j += n_threads) {
         s_lut[2 * j] = lut[max(j - 1, 0)];
         s_lut[2 * j + 1] = lut[min(j, size - 1)];
     }
+#else
+    for (int j = threadIdx.x; j < size + 2; j += n_threads) s_lut[j] = lut[min(max(j - 1, 0), size - 1)];
+#endif
+}
+// entry of lower tap i in [-1, size-1]: its two taps are at [0] and [1]
+__device__ __forceinline__ const float4 *lut_entry(const float4 *s_lut, int i) {
+    return PYVR_LUT_PAIRED ? s_lut + 2 * (i + 1) : s_lut + (i + 1);
+}
+__device__ __forceinline__ float4 lds128(const float4 *p) {   // one LDS.128 (keeps the compiler from splitting the fetch)
+    float4 v;
+    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+        : "r"((unsigned)__cvta_generic_to_shared(p)));
+    return v;
 }
 
 // Shade + composite one sample, STRICT arithmetic (volume.frag.glsl:96-115).  `k` holds the 8 corner texels.
@@ -190,7 +211,7 @@ __device__ __forceinline__ void shade_strict(const MarchArgs &a, const float4 *s
     const float density = PYVR_TRILERP(x);
     // texture(transfer_function_lut, vec2(density, 0.5)): linear, clamp-to-edge, row axis degenerate
     const Taps tl = axis_taps(density, a.lut_size);
-    const float4 l0 = s_lut[2 * (tl.i0 + 1)], l1 = s_lut[2 * (tl.i1 + 1)];
+    const float4 l0 = lut_entry(s_lut, tl.i0)[0], l1 = lut_entry(s_lut, tl.i1)[0];
     const float alpha_tf = lerpf(l0.w, l1.w, tl.f);
     const float alpha = 1.0f - expf(-alpha_tf * a.step / a.ref_step);
     const float cr = lerpf(l0.x, l1.x, tl.f), cg = lerpf(l0.y, l1.y, tl.f), cb = lerpf(l0.z, l1.z, tl.f);
@@ -216,8 +237,8 @@ __device__ __forceinline__ void shade_fast(const MarchArgs &a, const float4 *s_l
     const float x = density * (float)a.lut_size - 0.5f;     // the oracle's expression (cell_classify uses the same)
     const int i = __float2int_rd(x);
     const float f = x - (float)i;
-    const float4 *e = s_lut + 2 * (min(max(i, -1), a.lut_size - 1) + 1);
-    const float4 l0 = e[0], l1 = e[1];
+    const float4 *e = lut_entry(s_lut, min(max(i, -1), a.lut_size - 1));
+    const float4 l0 = lds128(e), l1 = lds128(e + 1);
     const float alpha_tf = lerpf(l0.w, l1.w, f);
     if (alpha_tf == 0.0f) return;
     const float alpha = 1.0f - ex2_approx(alpha_tf * a.exp2_scale);
@@ -248,6 +269,9 @@ __device__ __forceinline__ void index_slab(float X0, float D, float lo, float hi
     }
 }
 
+#ifndef PYVR_LANE_ARR
+#define PYVR_LANE_ARR 0
+#endif
 #ifndef PYVR_PF_DIST
 #define PYVR_PF_DIST 0     // samples ahead to prefetch (0 = off); PYVR_PF_LEVEL 1 = L1, 2 = L2
 #endif
@@ -281,24 +305,29 @@ __global__ void __launch_bounds__(CTA_THREADS, TEX ? PYVR_MARCH_MIN_BLOCKS_TEX :
 march_kernel(const __grid_constant__ MarchArgs a) {
     constexpr int ENTRY_BYTES = (HALF ? 8 : 16) << (PAIR ? 1 : 0);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int px = blockIdx.x * TILE_W + (warp % CTA_WX) * WARP_W + (lane % WARP_W);
-    const int py = blockIdx.y * TILE_H + (warp / CTA_WX) * WARP_H + (lane / WARP_W);
-    const bool in_image = px < a.width && py < a.height;
-
-    // image-space sharding: a CTA whose 64x64 tile group belongs to another rank only clears its pixels
+    // lane -> pixel inside the warp's 8x4 tile.  The L1 data stage serves a warp-wide load quarter-warp by
+    // quarter-warp (lanes 8q .. 8q+7); how many distinct entries those 8 lanes touch, and on which banks, decides
+    // how many cycles a pass takes (tools/bank_sim.py, profiles/r02_lane_ab.txt).
+#if PYVR_LANE_ARR == 1      // quarter-warp = 4x2 pixel block
+    const int lane_x = (lane & 3) + 4 * ((lane >> 3) & 1), lane_y = ((lane >> 2) & 1) + 2 * (lane >> 4);
+#elif PYVR_LANE_ARR == 2    // quarter-warp = 2x4 pixel block
+    const int lane_x = (lane & 1) + 2 * (lane >> 3), lane_y = (lane >> 1) & 3;
+#else                       // quarter-warp = one 8-pixel row
+    const int lane_x = lane % WARP_W, lane_y = lane / WARP_W;
+#endif
+    // image-space sharding (multi-GPU tiles): groups of 2^shift x 2^shift CTA tiles are dealt over the ranks along
+    // image rows, every row of groups shifted by one rank against the one below: owner(gx, gy) = (gx + gy) mod P.
+    // Only the owned tiles are launched: blockIdx.x enumerates this rank's groups of the row.
+    int tile_x = blockIdx.x;
     if (a.shard_count > 1) {
-        const int gx = (blockIdx.x * TILE_W) >> 6, gy = (blockIdx.y * TILE_H) >> 6;
-        const int groups_x = (a.width + 63) >> 6;
-        if ((gy * (groups_x + 1) + gx) % a.shard_count != a.shard_rank) {   // +1: skew the rows of groups
-            if (in_image) {
-                const size_t pix = ((size_t)blockIdx.z * a.height + py) * a.width + px;
-                const float4 keep = a.in_acc ? a.in_acc[pix] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                if (a.out_acc) a.out_acc[pix] = keep;
-                if (a.out8) a.out8[pix] = a.in_acc ? fragment_to_rgba8(keep.x, keep.y, keep.z, keep.w, a.flags) : make_uchar4(0, 0, 0, 0);
-            }
-            return;
-        }
+        const int sh = a.shard_shift, gy = blockIdx.y >> sh, k = blockIdx.x >> sh;
+        const int first = (a.shard_rank - gy % a.shard_count + a.shard_count) % a.shard_count;
+        tile_x = ((first + k * a.shard_count) << sh) + (blockIdx.x & ((1 << sh) - 1));
+        if (tile_x * TILE_W >= a.width) return;
     }
+    const int px = tile_x * TILE_W + (warp % CTA_WX) * WARP_W + lane_x;
+    const int py = blockIdx.y * TILE_H + (warp / CTA_WX) * WARP_H + lane_y;
+    const bool in_image = px < a.width && py < a.height;
 
     extern __shared__ float4 s_lut[];
     stage_lut(s_lut, a.lut, a.lut_size, CTA_THREADS);
@@ -641,7 +670,7 @@ march_kernel(const __grid_constant__ MarchArgs a) {
 
 template <bool STRICT, bool HALF, typename IDX, bool BRICK, bool PAIR, bool TEX = false>
 cudaError_t launch_one(const MarchArgs &a, int n_views, cudaStream_t stream) {
-    const size_t smem = ((size_t)a.lut_size + 1) * 2 * sizeof(float4);   // pair-packed LUT (stage_lut)
+    const size_t smem = lut_smem_bytes(a.lut_size);
     auto kern = march_kernel<STRICT, HALF, IDX, BRICK, PAIR, TEX>;
     // dynamic + static shared memory above the 48 KiB default needs the opt-in (static = the interval table)
     static size_t static_smem = ~(size_t)0;
@@ -655,7 +684,12 @@ cudaError_t launch_one(const MarchArgs &a, int n_views, cudaStream_t stream) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    dim3 grid((a.width + TILE_W - 1) / TILE_W, (a.height + TILE_H - 1) / TILE_H, n_views);
+    int tiles_x = (a.width + TILE_W - 1) / TILE_W;
+    if (a.shard_count > 1) {   // this rank's share of every row of tile groups (march_kernel, "image-space sharding")
+        const int group = 1 << a.shard_shift, groups_x = (tiles_x + group - 1) / group;
+        tiles_x = ((groups_x + a.shard_count - 1) / a.shard_count) * group;
+    }
+    dim3 grid(tiles_x, (a.height + TILE_H - 1) / TILE_H, n_views);
     kern<<<grid, CTA_THREADS, smem, stream>>>(a);
     return cudaGetLastError();
 }

@@ -77,6 +77,9 @@ SYMBOLS = {
     "pyvr_cuda_compute_normals": (_i, [_i, _vp, _vp, _i, _i, _i, _i, _fp]),
     "pyvr_cuda_composite_over": (_i, [_i, _vp, _vp, _vp, _c.c_size_t, _c.c_float, _vp]),
     "pyvr_cuda_finalize_rgba8": (_i, [_i, _vp, _vp, _c.c_size_t, _c.c_uint32, _vp]),
+    "pyvr_cuda_composite_finalize": (_i, [_i, _vp, _vp, _vp, _vp, _c.c_size_t, _c.c_float, _c.c_uint32, _vp]),
+    "pyvr_cuda_flag_signal": (_i, [_i, _vp, _c.c_uint32, _vp]),
+    "pyvr_cuda_flag_wait": (_i, [_i, _vp, _i, _c.c_uint32, _vp]),
     "pyvr_cuda_device_alloc": (_i, [_i, _c.c_size_t, _c.POINTER(_vp)]),
     "pyvr_cuda_device_free": (_i, [_i, _vp]),
     "pyvr_cuda_ipc_export": (_i, [_i, _vp, _vp]),
@@ -240,6 +243,21 @@ def composite_over(device: int, front_ptr: int, back_ptr: int, out_ptr: int, n_p
 
 def finalize_rgba8(device: int, accum_ptr: int, out_ptr: int, n_pixels: int, flags: int = 0, stream: int = 0) -> None:
     check(lib().pyvr_cuda_finalize_rgba8(device, _vp(accum_ptr), _vp(out_ptr), n_pixels, flags, _vp(stream)))
+
+
+def composite_finalize(device: int, front_ptr: int, back_ptr: int, accum_out_ptr: Optional[int], out_ptr: int, n_pixels: int,
+                       termination_alpha: float = 0.99, flags: int = 0, stream: int = 0) -> None:
+    """Last binary-swap round fused with finalize: ``out = rgba8(front over back)`` (``out`` may be peer memory)."""
+    check(lib().pyvr_cuda_composite_finalize(device, _vp(front_ptr), _vp(back_ptr), _vp(accum_out_ptr) if accum_out_ptr else None,
+                                             _vp(out_ptr), n_pixels, termination_alpha, flags, _vp(stream)))
+
+
+def flag_signal(device: int, flag_ptr: int, value: int, stream: int = 0) -> None:
+    check(lib().pyvr_cuda_flag_signal(device, _vp(flag_ptr), value & 0xFFFFFFFF, _vp(stream)))
+
+
+def flag_wait(device: int, flags_ptr: int, n_flags: int, value: int, stream: int = 0) -> None:
+    check(lib().pyvr_cuda_flag_wait(device, _vp(flags_ptr), n_flags, value & 0xFFFFFFFF, _vp(stream)))
 
 
 def stream_synchronize(device: int, stream: int = 0) -> None:

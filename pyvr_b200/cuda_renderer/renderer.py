@@ -286,9 +286,14 @@ class CudaVolumeRenderer:
         _cabi.check(self._lib.pyvr_cuda_read_texels(self._ctx, scalar.ctypes.data, normals.ctypes.data))
         return scalar, normals
 
-    def set_pixel_shard(self, rank: int, count: int) -> None:
-        """Image-space sharding: march only the 64x64 tile groups of ``rank`` (of ``count``); the frames
-        of all ranks add up to the full frame."""
+    def set_pixel_shard(self, rank: int, count: int, in_place: bool = False, group_shift: Optional[int] = None) -> None:
+        """Image-space sharding: march only the tile groups of ``rank`` (of ``count``).  By default the rest of
+        the frame is cleared, so the frames of all ranks add up to the full frame; ``in_place=True`` leaves the
+        other pixels untouched (all ranks write one shared frame, ``multi_gpu.TileSession``).  ``group_shift``: tile
+        groups of ``2^s x 2^s`` CTA tiles of 16x8 pixels (default 1)."""
+        if group_shift is not None:
+            _cabi.check(self._lib.pyvr_cuda_set_option(self._ctx, b"shard_shift", int(group_shift)))
+        _cabi.check(self._lib.pyvr_cuda_set_option(self._ctx, b"shard_in_place", int(bool(in_place))))
         _cabi.check(self._lib.pyvr_cuda_set_pixel_shard(self._ctx, int(rank), int(count)))
 
     def render_to_device(self, device_ptr: int) -> None:

@@ -32,7 +32,7 @@ import numpy as np
 __all__ = [
     "shard_views", "brick_grid", "rank_to_brick", "Brick", "split_bricks", "SwapRound", "binary_swap_plan",
     "final_piece", "front_is_low_side", "relay_order", "composite_in_process", "SortLastSession", "RelaySession",
-    "reduce_tile_frames",
+    "reduce_tile_frames", "PeerFlags", "TileSession",
 ]
 
 
@@ -238,6 +238,114 @@ def _slice(image, lo, hi, r, plan):
     return image[lo - base:hi - base]
 
 
+class PeerFlags:
+    """Stream-ordered flags between the ranks of one node: every rank owns ``slots x world`` uint32 counters in an
+    IPC-shared buffer; ``signal(dst, slot, v)`` stores ``v`` into ``dst``'s counter ``[slot][my rank]`` after everything
+    this rank's stream did before (system-scope release), ``wait(slot, src, v)`` stalls this rank's stream until its
+    own counter ``[slot][src]`` has reached ``v``.  Pairwise, device-side, no host synchronisation and no collective:
+    they replace the barrier / NCCL all-reduce fences around peer reads and writes (``pyvr_cuda_flag_signal`` /
+    ``pyvr_cuda_flag_wait``)."""
+
+    def __init__(self, dist, group, device: int, slots: int):
+        from .cuda_renderer import _cabi
+
+        self._cabi, self.device, self.slots = _cabi, device, int(slots)
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.own = _cabi.DeviceBuffer(self.slots * self.world * 4, device)
+        self.own.from_host(np.zeros(self.slots * self.world, np.uint32))
+        handles = [None] * self.world
+        dist.all_gather_object(handles, self.own.ipc_handle(), group=group)
+        self._handles, self._peers = handles, {}
+        dist.barrier(group=group)            # every counter is zeroed before anybody signals
+
+    def _ptr(self, rank: int) -> int:
+        if rank == self.rank:
+            return self.own.ptr
+        if rank not in self._peers:
+            self._peers[rank] = self._cabi.PeerBuffer(self._handles[rank], self.device)
+        return self._peers[rank].ptr
+
+    def signal(self, dst: int, slot: int, value: int, stream: int) -> None:
+        self._cabi.flag_signal(self.device, self._ptr(dst) + 4 * (slot * self.world + self.rank), value, stream)
+
+    def wait(self, slot: int, src: int, value: int, stream: int) -> None:
+        self._cabi.flag_wait(self.device, self.own.ptr + 4 * (slot * self.world + src), 1, value, stream)
+
+    def wait_all(self, slot: int, value: int, stream: int) -> None:
+        self._cabi.flag_wait(self.device, self.own.ptr + 4 * slot * self.world, self.world, value, stream)
+
+    def close(self) -> None:
+        for p in self._peers.values():
+            p.close()
+        self._peers = {}
+        if self.own is not None:
+            self.own.close()
+            self.own = None
+
+
+class TileSession:
+    """Image-space tiles over the ranks of one node (config C4), fused with the frame assembly: the volume is
+    replicated, every rank marches only its own tile groups (``set_pixel_shard(..., in_place=True)``: foreign
+    CTAs are not even launched) and its march kernel stores the finished RGBA8 pixels straight into rank
+    ``dst``'s frame through a CUDA-IPC peer mapping -- the 4 bytes per pixel cross NVLink from inside the
+    kernel, there is no separate reduce / gather pass.  Two peer flags per frame close it: every rank tells
+    ``dst`` its tiles are in, ``dst`` tells everybody the frame may be overwritten."""
+
+    def __init__(self, renderer, n_pixels: int, *, group=None, device: int = 0, dst: int = 0, group_shift: int = 1):
+        import torch
+        import torch.distributed as dist
+
+        from .cuda_renderer import _cabi
+
+        self.torch, self.dist, self.group, self.device, self.dst = torch, dist, group, device, dst
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.n_pixels, self.renderer, self._bound, self._frame_no = int(n_pixels), renderer, None, 0
+        _bind_stream(self, renderer)
+        renderer.set_pixel_shard(self.rank, self.world, in_place=True, group_shift=group_shift)
+        self._frame = _cabi.DeviceBuffer(self.n_pixels * 4, device) if self.rank == dst else None
+        if self._frame is not None:
+            self._frame.from_host(np.zeros(self.n_pixels * 4, np.uint8))      # rays that miss are never written
+        handles = [None] * self.world
+        dist.all_gather_object(handles, self._frame.ipc_handle() if self._frame is not None else None, group=group)
+        self._peer = None if self.rank == dst else _cabi.PeerBuffer(handles[dst], device)
+        self.frame_ptr = self._frame.ptr if self._frame is not None else self._peer.ptr
+        self.flags = PeerFlags(dist, group, device, slots=2)      # slot 0: "my tiles are in", slot 1: "frame released"
+
+    def render(self):
+        """One frame of the renderer's current camera.  Returns the device pointer of the assembled RGBA8 frame on
+        rank ``dst`` (valid in stream order), ``None`` elsewhere."""
+        stream = self.torch.cuda.current_stream().cuda_stream
+        self._frame_no += 1
+        f = self._frame_no
+        if f > 1 and self.rank != self.dst:
+            self.flags.wait(1, self.dst, f - 1, stream)          # dst has consumed the previous frame
+        self.renderer.render_to_device(self.frame_ptr)
+        self.flags.signal(self.dst, 0, f, stream)
+        if self.rank != self.dst:
+            return None
+        self.flags.wait_all(0, f, stream)
+        return self.frame_ptr
+
+    def release(self):
+        """Rank ``dst``: the frame returned by :meth:`render` has been consumed (in stream order)."""
+        if self.rank == self.dst:
+            stream = self.torch.cuda.current_stream().cuda_stream
+            for r in range(self.world):
+                if r != self.dst:
+                    self.flags.signal(r, 1, self._frame_no, stream)
+
+    def close(self):
+        self.torch.cuda.synchronize()
+        self.dist.barrier(group=self.group)
+        self.renderer.set_pixel_shard(0, 1)
+        self.flags.close()
+        if self._peer is not None:
+            self._peer.close()
+        if self._frame is not None:
+            self._frame.close()
+        self._peer = self._frame = None
+
+
 class RelaySession:
     """Exact sort-last: one accumulating image travels through the ranks in visibility order
     (:func:`relay_order`); every rank continues the march through its own brick
@@ -284,7 +392,8 @@ class SortLastSession:
 
     ``exchange``: ``"nccl"`` -- send/recv the half images through the process group, merge locally;
     ``"p2p"`` -- every rank's image lives in an IPC-shared ``cudaMalloc`` buffer and the merge kernel reads the
-    partner's half directly over NVLink (rounds are fenced with a barrier).  With the ``gloo`` backend (CPU
+    partner's half directly over NVLink; rounds are ordered by pairwise peer flags (:class:`PeerFlags`), the last
+    merge can be fused with the blend + RGBA8 quantisation and write into the destination rank's frame.  With the ``gloo`` backend (CPU
     tests) images are CPU tensors and ``over`` must be supplied.
     """
 
@@ -314,6 +423,7 @@ class SortLastSession:
         self.image = None          # float32 (n_pixels, 4)
         self._own = self._frame = None
         self._gather_out = self._gather_in = self._gather_frame = None
+        self._gather_dst = None
         if exchange == "p2p":
             self._setup_p2p()
         elif exchange != "nccl":
@@ -333,13 +443,13 @@ class SortLastSession:
         for step in self.plan:
             self._peers[step.partner] = _cabi.PeerBuffer(handles[step.partner][0], self.device)
         self._frame_peers = {}
-        self._fence_t = self.torch.zeros(1, dtype=self.torch.float32, device=f"cuda:{self.device}")
-
-    def _fence(self):
-        """Device-side barrier in stream order: the tiny all-reduce of rank A cannot complete before every
-        rank's kernel has started, i.e. before everything the ranks enqueued earlier has finished.  No host
-        synchronisation."""
-        self.dist.all_reduce(self._fence_t, group=self.group)
+        # pairwise peer flags instead of collective fences.  Slots: r (< K): "my image is ready for round r"
+        # (signalled to the partner of round r); K + r: "I have finished reading your image in round r" (release);
+        # 2K: "my piece of the frame is in" (to dst); 2K + 1: "frame consumed" (dst to all).  Values: frame number.
+        self._k = len(self.plan)
+        self._flags = PeerFlags(self.dist, self.group, self.device, slots=2 * self._k + 2)
+        self._frame_no = 0
+        self._finalized_to = None
 
     def _dst_frame_ptr(self, dst: int) -> int:
         from .cuda_renderer import _cabi
@@ -351,8 +461,11 @@ class SortLastSession:
         return self._frame_peers[dst].ptr
 
     def image_ptr(self) -> int:
-        """Device pointer the renderer writes its partial image to (``render_accum_to_device``)."""
+        """Device pointer the renderer writes its partial image to (``render_accum_to_device``).  Call once per
+        frame, right before the march: with the p2p exchange it also makes the stream wait until every partner has
+        finished reading the previous frame's image."""
         if self.exchange == "p2p":
+            self.begin_frame()
             return self._own.ptr
         if self.image is None:
             self.image = self.torch.zeros((self.n_pixels, 4), dtype=self.torch.float32, device=f"cuda:{self.device}")
@@ -363,15 +476,17 @@ class SortLastSession:
         plane = plane_position(self.shape, self.grid, step.axis, step.plane_brick)
         return front_is_low_side(camera_voxel, step.axis, plane) == step.low_side
 
-    def composite(self, camera_pos, image=None):
+    def composite(self, camera_pos, image=None, finalize_to: Optional[int] = None, flags: int = 0):
         """Merge the partial images of all ranks.  Returns ``((lo, hi), piece)``: this rank's fully composited
-        pixel range (a float32 ``(hi-lo, 4)`` tensor, or for ``"p2p"`` the device pointer of that range)."""
+        pixel range (a float32 ``(hi-lo, 4)`` tensor, or for ``"p2p"`` the device pointer of that range).
+        ``finalize_to`` (p2p only): fuse the blend + RGBA8 quantisation into the last merge and write the pixels
+        straight into that rank's frame; :meth:`gather_rgba8` then only closes the frame."""
         cam = camera_in_voxels(camera_pos, self.min_bounds, self.max_bounds, self.shape)
         if self._bound is None and self._over is None:
             # the march that filled the image ran on a stream this session does not know: wait for the device
             self.torch.cuda.synchronize()
         if self.exchange == "p2p":
-            return self._composite_p2p(cam)
+            return self._composite_p2p(cam, finalize_to, flags)
         torch, dist = self.torch, self.dist
         img = self.image if image is None else image
         base = 0
@@ -402,23 +517,50 @@ class SortLastSession:
                              self.term, stream)
         return out
 
-    def _composite_p2p(self, cam):
+    def _composite_p2p(self, cam, finalize_to=None, flags=0):
         from .cuda_renderer import _cabi
 
         torch = self.torch
         stream = torch.cuda.current_stream().cuda_stream
-        for step in self.plan:
-            # the partner's current image must be complete before it is read, and nobody may still be reading
-            # the range this rank is about to overwrite
-            self._fence()
+        k, fl = self._k, self._flags
+        self._frame_no += 1
+        f = self._frame_no
+        self._finalized_to = None
+        if self.plan:
+            fl.signal(self.plan[0].partner, 0, f, stream)          # the march (earlier in this stream) is complete
+        for r, step in enumerate(self.plan):
+            fl.wait(r, step.partner, f, stream)                     # the partner's image of this round is complete
             klo, khi = step.keep
             mine = self._own.ptr + klo * 16
             theirs = self._peers[step.partner].ptr + klo * 16
             front, back = (mine, theirs) if self._i_am_front(step, cam) else (theirs, mine)
-            # fused transfer + merge: the kernel loads the partner's half across NVLink and writes in place
-            _cabi.composite_over(self.device, front, back, mine, khi - klo, self.term, stream)
+            last = r == k - 1
+            if last and finalize_to is not None:
+                # fused transfer + merge + blend + RGBA8: the merged floats never go back to memory and the 4-byte
+                # pixels land in rank dst's frame across NVLink
+                _cabi.composite_finalize(self.device, front, back, None, self._dst_frame_ptr(finalize_to) + klo * 4,
+                                         khi - klo, self.term, flags, stream)
+                self._finalized_to = finalize_to
+            else:
+                # fused transfer + merge: the kernel loads the partner's half across NVLink and writes in place
+                _cabi.composite_over(self.device, front, back, mine, khi - klo, self.term, stream)
+            fl.signal(step.partner, k + r, f, stream)               # done reading the partner's image
+            if not last:
+                fl.signal(self.plan[r + 1].partner, r + 1, f, stream)
         lo, hi = self.plan[-1].keep if self.plan else (0, self.n_pixels)
         return (lo, hi), self._own.ptr + lo * 16
+
+    def begin_frame(self):
+        """p2p exchange: call before the march of the next frame (in stream order).  The partial image may be
+        overwritten only after every partner has finished reading it, and a piece may be written into rank dst's frame
+        only after dst has consumed the previous frame."""
+        if self.exchange != "p2p" or self._frame_no == 0:
+            return
+        stream = self.torch.cuda.current_stream().cuda_stream
+        for r, step in enumerate(self.plan):
+            self._flags.wait(self._k + r, step.partner, self._frame_no, stream)
+        if self._gather_dst is not None and self.rank != self._gather_dst:
+            self._flags.wait(2 * self._k + 1, self._gather_dst, self._frame_no, stream)
 
     # -- final frame -----------------------------------------------------------------------------
     def gather_rgba8(self, piece_range, piece, flags: int = 0, dst: int = 0):
@@ -431,13 +573,22 @@ class SortLastSession:
         lo, hi = piece_range
         n = hi - lo
         if self.exchange == "p2p":
-            # every rank writes its finalised piece straight into rank dst's frame (peer stores over NVLink);
-            # the closing fence tells dst the frame is complete and everyone that its image may be reused
-            _cabi.finalize_rgba8(self.device, piece, self._dst_frame_ptr(dst) + lo * 4, n, flags,
-                                 torch.cuda.current_stream().cuda_stream)
-            self._fence()
+            # every rank writes its finalised piece straight into rank dst's frame (peer stores over NVLink), unless the
+            # last merge already did; then one flag per rank tells dst the frame is complete
+            stream = torch.cuda.current_stream().cuda_stream
+            if self._finalized_to != dst:
+                _cabi.finalize_rgba8(self.device, piece, self._dst_frame_ptr(dst) + lo * 4, n, flags, stream)
+            k = self._k
+            self._gather_dst = dst
+            self._flags.signal(dst, 2 * k, self._frame_no, stream)
+            if self.rank == dst:
+                self._flags.wait_all(2 * k, self._frame_no, stream)
+                for r in range(self.world):      # the frame is complete; peers may write the next one once dst moves on
+                    if r != dst:
+                        self._flags.signal(r, 2 * k + 1, self._frame_no, stream)
             if self._bound is None:       # the next march may run on another stream: it must not overwrite the image
                 torch.cuda.current_stream().synchronize()   # while a peer's merge or this finalize still reads it
+                self.dist.barrier(group=self.group)
             return self._frame.ptr if self.rank == dst else None
         per = -(-self.n_pixels // self.world)            # pieces differ by at most one pixel: pad to the largest
         if self._gather_out is None:
@@ -466,6 +617,9 @@ class SortLastSession:
         for p in list(self._peers.values()) + list(getattr(self, "_frame_peers", {}).values()):
             p.close()
         self._peers, self._frame_peers = {}, {}
+        if getattr(self, "_flags", None) is not None:
+            self._flags.close()
+            self._flags = None
         for buf in (self._own, self._frame):
             if buf is not None:
                 buf.close()

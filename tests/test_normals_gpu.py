@@ -37,7 +37,9 @@ def test_double_sphere_128_hash(golden_dir):
 
 
 @pytest.mark.parametrize("shape", [(1, 1, 1), (1, 5, 8), (7, 1, 4), (3, 3, 3), (5, 6, 7), (16, 12, 20),
-                                   (33, 17, 64), (64, 64, 64), (2, 2, 4)])
+                                   (33, 17, 64), (64, 64, 64), (2, 2, 4),
+                                   # TMA path (n2 % 4 == 0): partial tiles in y and z, chunk seams (32 planes), tiny volumes
+                                   (2, 2, 8), (3, 9, 8), (35, 10, 12), (65, 19, 140), (34, 8, 256), (70, 9, 260), (97, 33, 132)])
 def test_ragged_and_vector_paths_vs_oracle(shape):
     rng = np.random.default_rng(sum(shape))
     vol = (rng.standard_normal(shape) * 3).astype(np.float32)
