@@ -32,7 +32,8 @@ import numpy as np
 __all__ = [
     "shard_views", "brick_grid", "rank_to_brick", "Brick", "split_bricks", "SwapRound", "binary_swap_plan",
     "final_piece", "front_is_low_side", "relay_order", "composite_in_process", "SortLastSession", "RelaySession",
-    "reduce_tile_frames", "PeerFlags", "TileSession",
+    "reduce_tile_frames", "PeerFlags", "TileSession", "halo_block", "brick_normals", "slab_range",
+    "compute_normal_volume_sharded",
 ]
 
 
@@ -636,6 +637,83 @@ def _bind_stream(session, renderer):
     if session._bound != (id(renderer), stream):
         renderer.set_stream(stream)
         session._bound = (id(renderer), stream)
+
+
+# --------------------------------------------------------------------------------------------------
+# compute_normal_volume across ranks (SURVEY.md section 8 e, last row)
+# --------------------------------------------------------------------------------------------------
+def _device_normals(block: np.ndarray, device: int) -> np.ndarray:
+    from .cuda_renderer import _cabi
+
+    return _cabi.compute_normals_host(block, device=device)
+
+
+def halo_block(volume: np.ndarray, lo: Sequence[int], hi: Sequence[int]):
+    """Sub-block ``[lo, hi)`` of ``volume`` extended by one voxel on every side that is not a face of the volume.
+    Returns ``(block, inner)``: ``block[inner]`` is the sub-block itself.  Central differences of the sub-block's
+    voxels only reach into that one-voxel halo, and where the sub-block touches a face of the volume the face of
+    ``block`` coincides with it, so the one-sided differences of ``np.gradient`` land on the same voxels."""
+    ext_lo = [max(int(a) - 1, 0) for a in lo]
+    ext_hi = [min(int(b) + 1, int(n)) for b, n in zip(hi, volume.shape)]
+    block = np.ascontiguousarray(volume[tuple(slice(a, b) for a, b in zip(ext_lo, ext_hi))], dtype=np.float32)
+    inner = tuple(slice(int(a) - e, int(b) - e) for a, b, e in zip(lo, hi, ext_lo))
+    return block, inner
+
+
+def brick_normals(volume: np.ndarray, brick: Brick, *, device: int = 0, normals_fn: Optional[Callable] = None) -> np.ndarray:
+    """``compute_normal_volume(volume)[brick.slices()]`` computed from the brick's own voxels plus a one-voxel halo
+    (K2 on ``device``): bit-identical to slicing the whole normal volume, without ever building it.  This is what a
+    sort-last rank feeds ``VolumeRenderer.load_brick`` when the scalar volume is host-supplied (pyvr/datasets/
+    synthetic.py:109-122 is a 3-point stencil per axis)."""
+    lo = brick.origin
+    hi = tuple(o + d for o, d in zip(brick.origin, brick.dims))
+    block, inner = halo_block(volume, lo, hi)
+    fn = normals_fn or (lambda b: _device_normals(b, device))
+    return np.ascontiguousarray(fn(block)[inner])
+
+
+def slab_range(n0: int, rank: int, world: int) -> Tuple[int, int]:
+    """Planes of axis 0 that ``rank`` computes when a volume is cut into ``world`` slabs."""
+    return (n0 * rank) // world, (n0 * (rank + 1)) // world
+
+
+def compute_normal_volume_sharded(volume: np.ndarray, *, group=None, device: int = 0,
+                                  normals_fn: Optional[Callable] = None, gather: bool = True):
+    """``compute_normal_volume`` split over the ranks of a process group: rank ``r`` computes the slab
+    ``slab_range(n0, r, P)`` of axis 0 from its planes plus a one-plane halo on each cut side, then the slabs are
+    all-gathered (``gather=False``: returns ``((x0, x1), slab)`` only).  Every rank holds the scalar volume (it is a
+    quarter of the size of its normals); the result is bit-identical to the single-device function.  ``normals_fn``
+    replaces the CUDA stencil (the CPU tests pass the oracle)."""
+    import torch
+    import torch.distributed as dist
+
+    volume = np.asarray(volume)
+    if volume.ndim != 3:
+        raise ValueError("Volume data must be 3D")
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    n0 = volume.shape[0]
+    if n0 < world:
+        raise ValueError(f"axis 0 of {n0} planes cannot be cut into {world} slabs")
+    x0, x1 = slab_range(n0, rank, world)
+    block, inner = halo_block(volume, (x0, 0, 0), (x1,) + tuple(volume.shape[1:]))
+    fn = normals_fn or (lambda b: _device_normals(b, device))
+    slab = np.ascontiguousarray(fn(block)[inner])
+    if not gather:
+        return (x0, x1), slab
+    on_gpu = dist.get_backend(group) == "nccl"
+    out = np.empty(volume.shape + (3,), dtype=np.float32)
+    planes = max(slab_range(n0, r, world)[1] - slab_range(n0, r, world)[0] for r in range(world))
+    pad = np.zeros((planes,) + slab.shape[1:], np.float32)       # all_gather wants equal shapes: pad the short slabs
+    pad[:slab.shape[0]] = slab
+    mine = torch.from_numpy(pad)
+    if on_gpu:
+        mine = mine.cuda(device)
+    parts = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine, group=group)
+    for r in range(world):
+        a, b = slab_range(n0, r, world)
+        out[a:b] = parts[r][:b - a].cpu().numpy()
+    return out
 
 
 def reduce_tile_frames(frame, dst: int = 0, group=None):

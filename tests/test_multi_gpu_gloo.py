@@ -63,3 +63,41 @@ def test_sort_last_session_over_gloo(tmp_path, world, cam):
     assert want[:, 3].max() > 0.3 and np.allclose(got, want, atol=3e-6)
     frame = np.load(tmp_path / "frame.npy")
     assert np.array_equal(frame, np.tile(np.arange(1, world + 1, dtype=np.uint8), 64 // world + 1)[:64])
+
+
+def _normals_worker(rank, world, port, shape, result_dir):
+    import oracle
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        vol = (np.random.default_rng(5).standard_normal(shape) * 2).astype(np.float32)
+        got = mg.compute_normal_volume_sharded(vol, normals_fn=oracle.normals)
+        np.save(os.path.join(result_dir, f"normals_{rank}.npy"), got)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,shape", [(2, (9, 6, 8)), (4, (10, 5, 12)), (2, (2, 3, 4))])
+def test_sharded_normal_volume_is_bit_identical(tmp_path, world, shape):
+    """Slab split of compute_normal_volume with a one-plane halo (SURVEY.md section 8 e): every rank ends up with
+    exactly the single-process normal volume."""
+    import oracle
+
+    mp.spawn(_normals_worker, args=(world, _free_port(), shape, str(tmp_path)), nprocs=world, join=True)
+    vol = (np.random.default_rng(5).standard_normal(shape) * 2).astype(np.float32)
+    want = oracle.normals(vol)
+    for r in range(world):
+        got = np.load(tmp_path / f"normals_{r}.npy")
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), r
+
+
+def test_brick_normals_equal_the_sliced_normal_volume():
+    import oracle
+
+    vol = (np.random.default_rng(9).standard_normal((12, 10, 16)) * 2).astype(np.float32)
+    want = oracle.normals(vol)
+    for world in (2, 4, 8):
+        for b in mg.split_bricks(vol.shape, mg.brick_grid(world)):
+            got = mg.brick_normals(vol, b, normals_fn=oracle.normals)
+            assert np.array_equal(got.view(np.uint32), want[b.slices()].view(np.uint32)), (world, b.coord)

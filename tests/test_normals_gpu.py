@@ -62,3 +62,20 @@ def test_volume_compute_normals_method_and_dtype_cast():
         v.compute_normals("sobel")
     with pytest.raises(ValueError, match="must be 3D"):
         compute_normal_volume(np.zeros((4, 4), np.float32))
+
+
+def test_brick_and_slab_normals_match_the_whole_volume():
+    """Multi-GPU split of K2 (SURVEY.md section 8 e): a brick / slab plus a one-voxel halo gives exactly the slice
+    of the whole normal volume (here every 'rank' runs on the one visible GPU)."""
+    from pyvr_b200 import multi_gpu as mg
+
+    vol = create_sample_volume(64, "double_sphere")
+    want = compute_normal_volume(vol)
+    for b in mg.split_bricks(vol.shape, mg.brick_grid(8)):
+        got = mg.brick_normals(vol, b)
+        assert np.array_equal(got.view(np.uint32), want[b.slices()].view(np.uint32)), b.coord
+    for rank in range(3):
+        x0, x1 = mg.slab_range(64, rank, 3)
+        block, inner = mg.halo_block(vol, (x0, 0, 0), (x1, 64, 64))
+        got = compute_normal_volume(block)[inner]
+        assert np.array_equal(got.view(np.uint32), want[x0:x1].view(np.uint32)), rank
