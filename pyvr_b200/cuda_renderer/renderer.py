@@ -24,6 +24,7 @@ from ..lighting import Light
 from ..transferfunctions import build_rgba_lut
 from ..volume import Volume
 from . import _cabi
+from .manager import CudaManager
 
 # The shader's stop test is a literal (volume.frag.glsl:87); RenderConfig.opacity_threshold never
 # reaches it (renderer.py:303-309).
@@ -84,19 +85,22 @@ class CudaVolumeRenderer:
         self._honor_termination = bool(honor_config_termination)
         self._hwtex = bool(hardware_filtering)
         self._lib = _cabi.lib()
-        self._staging = None
-        self._ctx = ctypes.c_void_p()
-        _cabi.check(self._lib.pyvr_cuda_create(self.device, int(width), int(height), ctypes.byref(self._ctx)))
-        self._push_params()
+        # the resource layer, driven through ModernGLManager's method names (renderer.py:89-105)
+        self.gl_manager = CudaManager(width, height, device=self.device, texel_format=self._texel_format,
+                                      flags=self._flags(), termination_alpha=self._termination_alpha())
+        self._ctx = self.gl_manager.ctx
+        self.gl_manager.load_shaders()
+        self._update_render_config()
+        self.gl_manager.set_uniform_vector("volume_min_bounds", (-0.5, -0.5, -0.5))
+        self.gl_manager.set_uniform_vector("volume_max_bounds", (0.5, 0.5, 0.5))
+        self._update_light()
 
     # -- resource life cycle -------------------------------------------------------------
     def close(self) -> None:
-        ctx, self._ctx = getattr(self, "_ctx", None), None
-        if ctx:
-            self._lib.pyvr_cuda_destroy(ctx)
-        staging, self._staging = getattr(self, "_staging", None), None
-        if staging is not None:
-            staging.close()
+        manager = getattr(self, "gl_manager", None)
+        if manager is not None and getattr(manager, "ctx", None):
+            manager.cleanup()
+        self._ctx = None
 
     def __del__(self):
         try:
@@ -110,59 +114,52 @@ class CudaVolumeRenderer:
     def __exit__(self, *exc):
         self.close()
 
-    # -- reference API ---------------------------------------------------------------------
+    # -- reference API (same calls into the manager, in the same order, as renderer.py:107-316) ----------------
     def load_volume(self, volume: Volume) -> None:
         if not _is_a(volume, Volume, "Volume"):
             raise TypeError(
                 f"Expected Volume instance, got {type(volume)}. "
                 "Create a Volume instance: from pyvr.volume import Volume; "
                 "volume = Volume(data=your_array)")
-        data = volume.data
-        if data.ndim != 3:
-            raise ValueError("Volume data must be 3D")
-        data = np.ascontiguousarray(data, dtype=np.float32)  # manager.py:91-92 casts to float32
-        normals = None
-        if volume.has_normals:
-            if volume.normals.shape[-1] != 3:
-                raise ValueError("Normal volume must have 3 channels (last dimension).")
-            normals = np.ascontiguousarray(volume.normals, dtype=np.float32)
         self.volume = volume
-        bmin, bmax = _cabi.vec3(volume.min_bounds), _cabi.vec3(volume.max_bounds)
-        _cabi.check(self._lib.pyvr_cuda_upload_volume(
-            self._ctx, data.ctypes.data, normals.ctypes.data if normals is not None else None,
-            data.shape[0], data.shape[1], data.shape[2], _cabi.f32_ptr(bmin), _cabi.f32_ptr(bmax),
-            self._texel_format, 0))
+        texture_unit = self.gl_manager.create_volume_texture(volume.data)
+        self.gl_manager.set_uniform_int("volume_texture", texture_unit)
+        self.gl_manager.set_uniform_vector("volume_min_bounds", tuple(volume.min_bounds))
+        self.gl_manager.set_uniform_vector("volume_max_bounds", tuple(volume.max_bounds))
+        if volume.has_normals:
+            normal_unit = self.gl_manager.create_normal_texture(volume.normals)
+            self.gl_manager.set_uniform_int("normal_volume", normal_unit)
 
     def set_camera(self, camera: Camera) -> None:
         if not _is_a(camera, Camera, "Camera"):
             raise TypeError(f"Expected Camera instance, got {type(camera)}")
         self.camera = camera
         aspect = self.width / self.height
-        view = np.ascontiguousarray(camera.get_view_matrix(), dtype=np.float32).reshape(16)
-        proj = np.ascontiguousarray(camera.get_projection_matrix(aspect), dtype=np.float32).reshape(16)
+        view_matrix = camera.get_view_matrix()
+        projection_matrix = camera.get_projection_matrix(aspect)
         position, _ = camera.get_camera_vectors()
-        pos = _cabi.vec3(position)
-        _cabi.check(self._lib.pyvr_cuda_set_camera(
-            self._ctx, _cabi.f32_ptr(view), _cabi.f32_ptr(proj), _cabi.f32_ptr(pos)))
+        self.gl_manager.set_uniform_matrix("view_matrix", view_matrix)
+        self.gl_manager.set_uniform_matrix("projection_matrix", projection_matrix)
+        self.gl_manager.set_uniform_vector("camera_pos", tuple(position))
 
     def set_light(self, light: Light) -> None:
         if not _is_a(light, Light, "Light"):
             raise TypeError(f"Expected Light instance, got {type(light)}")
         self.light = light
-        self._push_params()
+        self._update_light()
 
     def set_transfer_functions(self, color_transfer_function, opacity_transfer_function,
                                size: Optional[int] = None) -> None:
-        lut = np.ascontiguousarray(
-            build_rgba_lut(color_transfer_function, opacity_transfer_function, size), dtype=np.float32)
-        _cabi.check(self._lib.pyvr_cuda_set_lut(self._ctx, lut.ctypes.data, lut.shape[0]))
+        rgba_tex_unit = self.gl_manager.create_rgba_transfer_function_texture(
+            color_transfer_function, opacity_transfer_function, size)
+        self.gl_manager.set_uniform_int("transfer_function_lut", rgba_tex_unit)
 
     def render(self) -> bytes:
         """Raw RGBA8 pixels, ``width*height*4`` bytes, bottom row first."""
-        if self._staging is None:      # page-locked read-back target: full PCIe rate, one copy into the bytes object
-            self._staging = _cabi.PinnedBuffer(self.width * self.height * 4)
-        _cabi.check(self._lib.pyvr_cuda_render(self._ctx, self._staging.array.ctypes.data, 0))
-        return self._staging.array.tobytes()
+        self.gl_manager.clear_framebuffer(0.0, 0.0, 0.0, 0.0)
+        self.gl_manager.setup_blending()
+        self.gl_manager.render_quad()
+        return self.gl_manager.read_pixels()
 
     def render_to_pil(self, data=None):
         from PIL import Image
@@ -176,7 +173,7 @@ class CudaVolumeRenderer:
         if not _is_a(config, RenderConfig, "RenderConfig"):
             raise TypeError(f"Expected RenderConfig instance, got {type(config)}")
         self.config = config
-        self._push_params()
+        self._update_render_config()
 
     def get_config(self):
         return self.config
@@ -190,13 +187,23 @@ class CudaVolumeRenderer:
     def get_camera(self) -> Optional[Camera]:
         return self.camera
 
+    def _update_render_config(self):
+        self.gl_manager.set_uniform_float("step_size", self.config.step_size)
+        self.gl_manager.set_uniform_int("max_steps", self.config.max_steps)
+        self.gl_manager.set_uniform_float("reference_step_size", self.config.reference_step_size)
+        if hasattr(self.gl_manager, "set_march_options"):     # non-parity opt-in follows the config (see __init__)
+            self.gl_manager.set_march_options(termination_alpha=self._termination_alpha())
+
+    def _update_light(self):
+        self.gl_manager.set_uniform_float("ambient_light", self.light.ambient_intensity)
+        self.gl_manager.set_uniform_float("diffuse_light", self.light.diffuse_intensity)
+        self.gl_manager.set_uniform_vector("light_position", tuple(self.light.position))
+        self.gl_manager.set_uniform_vector("light_target", tuple(self.light.target))
+
     # -- additive API ----------------------------------------------------------------------
     def set_lut(self, rgba: np.ndarray) -> None:
         """Upload a ready ``(size, 4) float32`` RGBA table."""
-        lut = np.ascontiguousarray(rgba, dtype=np.float32)
-        if lut.ndim != 2 or lut.shape[1] != 4:
-            raise ValueError("LUT must have shape (size, 4)")
-        _cabi.check(self._lib.pyvr_cuda_set_lut(self._ctx, lut.ctypes.data, lut.shape[0]))
+        self.gl_manager.set_uniform_int("transfer_function_lut", self.gl_manager.create_lut_texture(rgba))
 
     def render_array(self, out: Optional[np.ndarray] = None) -> np.ndarray:
         """``render()`` into a ``(height, width, 4) uint8`` array (pinned or not); no ``bytes`` copy."""
@@ -205,6 +212,7 @@ class CudaVolumeRenderer:
         if (not isinstance(out, np.ndarray) or out.dtype != np.uint8 or not out.flags.c_contiguous
                 or not out.flags.writeable or out.nbytes < self.height * self.width * 4):
             raise ValueError("out must be a writeable C-contiguous uint8 array of at least height*width*4 bytes")
+        self._sync()
         _cabi.check(self._lib.pyvr_cuda_render(self._ctx, out.ctypes.data, 0))
         return out
 
@@ -228,6 +236,7 @@ class CudaVolumeRenderer:
             if cameras is None:
                 raise ValueError("render_batch needs `cameras` or `views`")
             views = self.make_views(cameras)
+        self._sync()
         n = len(views)
         if device_ptr is not None:
             _cabi.check(self._lib.pyvr_cuda_render_batch(self._ctx, views, n, ctypes.c_void_p(device_ptr), 1))
@@ -260,6 +269,7 @@ class CudaVolumeRenderer:
             self._ctx, data.ctypes.data, normals.ctypes.data if normals is not None else None,
             i3(data.shape), i3(global_shape), i3(origin), i3(own_lo), i3(own_hi),
             _cabi.f32_ptr(bmin), _cabi.f32_ptr(bmax), self._texel_format, 0))
+        self.gl_manager.adopt_device_volume()
 
     def generate_volume(self, size: int, shape: str = "double_sphere", min_bounds=(-0.5, -0.5, -0.5),
                         max_bounds=(0.5, 0.5, 0.5), brick=None) -> float:
@@ -277,10 +287,12 @@ class CudaVolumeRenderer:
             self._ctx, _cabi.SHAPES[shape], int(size), *args, _cabi.f32_ptr(bmin), _cabi.f32_ptr(bmax),
             self._texel_format, ctypes.byref(ms)))
         self.volume = None
+        self.gl_manager.adopt_device_volume()
         return ms.value
 
     def read_texels(self, shape) -> tuple:
         """Test aid: the stored block unpacked to ``(scalar (shape), normals (shape + (3,)))`` float32."""
+        self._sync()
         scalar = np.empty(tuple(shape), dtype=np.float32)
         normals = np.empty(tuple(shape) + (3,), dtype=np.float32)
         _cabi.check(self._lib.pyvr_cuda_read_texels(self._ctx, scalar.ctypes.data, normals.ctypes.data))
@@ -298,10 +310,12 @@ class CudaVolumeRenderer:
 
     def render_to_device(self, device_ptr: int) -> None:
         """``render()`` into a device buffer of ``width*height*4`` bytes."""
+        self._sync()
         _cabi.check(self._lib.pyvr_cuda_render(self._ctx, ctypes.c_void_p(device_ptr), 1))
 
     def render_accum_to_device(self, device_ptr: int) -> None:
         """Pre-blend fragment colours (``width*height`` float4) into a device buffer: a partial image."""
+        self._sync()
         _cabi.check(self._lib.pyvr_cuda_render_accum(self._ctx, ctypes.c_void_p(device_ptr), 1))
 
     def render_tensor(self, cameras=None, out=None):
@@ -317,6 +331,7 @@ class CudaVolumeRenderer:
         if tuple(out.shape) != shape or out.dtype != torch.uint8 or not out.is_contiguous() or out.device.index != self.device:
             raise ValueError(f"out must be a contiguous uint8 CUDA tensor of shape {shape} on device {self.device}")
         if n is None:
+            self._sync()
             _cabi.check(self._lib.pyvr_cuda_render(self._ctx, ctypes.c_void_p(out.data_ptr()), 1))
         else:
             self.render_batch(cameras, device_ptr=out.data_ptr())
@@ -325,11 +340,13 @@ class CudaVolumeRenderer:
     def render_accum_relay(self, in_ptr: Optional[int], out_ptr: int) -> None:
         """Sort-last relay: continue the device image ``in_ptr`` (fragment colours of the bricks in front;
         ``None`` for the first brick) through this renderer's brick into ``out_ptr`` (may be the same)."""
+        self._sync()
         _cabi.check(self._lib.pyvr_cuda_render_accum_relay(
             self._ctx, ctypes.c_void_p(in_ptr) if in_ptr else None, ctypes.c_void_p(out_ptr)))
 
     def render_accum(self) -> np.ndarray:
         """Fragment colour before blending: ``(height, width, 4) float32`` = (acc_rgb, acc_a)."""
+        self._sync()
         out = np.empty((self.height, self.width, 4), dtype=np.float32)
         _cabi.check(self._lib.pyvr_cuda_render_accum(self._ctx, out.ctypes.data, 0))
         return out
@@ -353,17 +370,7 @@ class CudaVolumeRenderer:
             return 2.0  # never reached
         return float(self.config.opacity_threshold)
 
-    def _push_params(self) -> None:
-        """``_update_render_config`` + ``_update_light`` of the reference (renderer.py:303-316)."""
-        p = _cabi.Params()
-        p.step_size = float(self.config.step_size)
-        p.max_steps = int(self.config.max_steps)
-        p.reference_step_size = float(self.config.reference_step_size)
-        p.ambient = float(self.light.ambient_intensity)
-        p.diffuse = float(self.light.diffuse_intensity)
-        p.light_position[:] = [float(v) for v in _cabi.vec3(self.light.position)]
-        p.light_target[:] = [float(v) for v in _cabi.vec3(self.light.target)]
-        p.termination_alpha = self._termination_alpha()
+    def _flags(self) -> int:
         flags = 0
         if self._strict:
             flags |= _cabi.FLAG_STRICT
@@ -371,8 +378,12 @@ class CudaVolumeRenderer:
             flags |= _cabi.FLAG_ESS
         if self._hwtex and not self._strict:
             flags |= _cabi.FLAG_HWTEX
-        p.flags = flags
-        _cabi.check(self._lib.pyvr_cuda_set_params(self._ctx, ctypes.byref(p)))
+        return flags
+
+    def _sync(self) -> None:
+        """Additive entry points call the C ABI directly: first bring the device in line with what the reference
+        API recorded in the manager (volume, camera, uniforms)."""
+        self.gl_manager.flush()
 
 
 # Same alias the reference exports (renderer.py:320).
