@@ -173,13 +173,12 @@ struct Accum {
     float r, g, b, a;
 };
 
-// The transfer-function LUT in shared memory.  PYVR_LUT_PAIRED (default): pair-packed like the z-pair texels --
-// entry j (0 <= j <= size) holds {lut[max(j-1, 0)], lut[min(j, size-1)]}, i.e. both taps of a fetch whose lower tap
-// floor(x) is j - 1; a fetch is one clamp of floor(x) to [-1, size-1] and two LDS.128 at one address, and
-// out-of-range densities land on an entry whose halves are equal (CLAMP_TO_EDGE).  Unpaired: entry j = lut[j - 1]
-// with one apron entry on each side (same clamp, taps 16 bytes apart).
+// The transfer-function LUT in shared memory with one apron entry on each side: entry j = lut[clamp(j - 1)], so a
+// fetch is one clamp of floor(x) to [-1, size-1] and two LDS.128 sixteen bytes apart, and out-of-range densities
+// land on two equal taps (CLAMP_TO_EDGE).  PYVR_LUT_PAIRED=1 (A/B only) pair-packs it like the z-pair texels: entry
+// j holds {lut[max(j-1, 0)], lut[min(j, size-1)]}.
 #ifndef PYVR_LUT_PAIRED
-#define PYVR_LUT_PAIRED 1
+#define PYVR_LUT_PAIRED 0   // unpaired: half the shared memory and fewer LDS bank conflicts (+1 % on C3, profiles/r02_lane_ab.txt)
 #endif
 __host__ __device__ constexpr size_t lut_smem_bytes(int size) {
     return PYVR_LUT_PAIRED ? ((size_t)size + 1) * 2 * sizeof(float4) : ((size_t)size + 2) * sizeof(float4);
@@ -232,7 +231,7 @@ __device__ __forceinline__ void shade_strict(const MarchArgs &a, const float4 *s
 // LUT fetch + shading + front-to-back compositing of the fast paths.  density and the (not yet normalised)
 // normal are already filtered.  Returns without touching acc when alpha_tf == 0: such a sample contributes
 // exactly +0 to every accumulator.
-__device__ __forceinline__ void shade_fast(const MarchArgs &a, const float4 *s_lut, float density, float nx, float ny,
+__device__ __forceinline__ bool shade_fast(const MarchArgs &a, const float4 *s_lut, float density, float nx, float ny,
                                            float nz, Accum &acc) {
     const float x = density * (float)a.lut_size - 0.5f;     // the oracle's expression (cell_classify uses the same)
     const int i = __float2int_rd(x);
@@ -240,7 +239,7 @@ __device__ __forceinline__ void shade_fast(const MarchArgs &a, const float4 *s_l
     const float4 *e = lut_entry(s_lut, min(max(i, -1), a.lut_size - 1));
     const float4 l0 = lds128(e), l1 = lds128(e + 1);
     const float alpha_tf = lerpf(l0.w, l1.w, f);
-    if (alpha_tf == 0.0f) return;
+    if (alpha_tf == 0.0f) return false;
     const float alpha = 1.0f - ex2_approx(alpha_tf * a.exp2_scale);
     const f32x2 f2 = pack2(f, f);
     float cr, cg;
@@ -255,7 +254,25 @@ __device__ __forceinline__ void shade_fast(const MarchArgs &a, const float4 *s_l
     acc.g = fmaf(t, cg * light * alpha, acc.g);
     acc.b = fmaf(t, cb * light * alpha, acc.b);
     acc.a = fmaf(t, alpha, acc.a);
+    return true;
 }
+
+// Opacity of a sample from its density alone (the same expressions as shade_fast): two 4-byte LUT reads.
+__device__ __forceinline__ float lut_alpha(const MarchArgs &a, const float4 *s_lut, float density) {
+    const float x = density * (float)a.lut_size - 0.5f;
+    const int i = __float2int_rd(x);
+    const float f = x - (float)i;
+    const float4 *e = lut_entry(s_lut, min(max(i, -1), a.lut_size - 1));
+    return lerpf(e[0].w, e[1].w, f);
+}
+
+// The scalar of the texel at p (binary32, or binary16 widened): 4 (2) bytes instead of the 16 (8) of the texel.
+template <bool HALF>
+__device__ __forceinline__ float load_scalar_at(const char *p) {
+    if constexpr (HALF) return __half2float(__ushort_as_half(__ldg(reinterpret_cast<const unsigned short *>(p))));
+    else return __ldg(reinterpret_cast<const float *>(p));
+}
+
 
 // Index interval on which lo <= X0 + i*D <= hi, intersected into [enter, exit].
 __device__ __forceinline__ void index_slab(float X0, float D, float lo, float hi, float &enter, float &exit) {
@@ -270,7 +287,10 @@ __device__ __forceinline__ void index_slab(float X0, float D, float lo, float hi
 }
 
 #ifndef PYVR_LANE_ARR
-#define PYVR_LANE_ARR 0
+#define PYVR_LANE_ARR 1     // measured on C3 (profiles/r02_lane_ab.txt): 4x2 blocks 477, 2x4 blocks 448-470, rows 449 Gsamples/s
+#endif
+#ifndef PYVR_DENSITY_FIRST
+#define PYVR_DENSITY_FIRST 1
 #endif
 #ifndef PYVR_PF_DIST
 #define PYVR_PF_DIST 0     // samples ahead to prefetch (0 = off); PYVR_PF_LEVEL 1 = L1, 2 = L2
@@ -574,6 +594,7 @@ march_kernel(const __grid_constant__ MarchArgs a) {
             }
         }
         int run_end = i;                  // first index past the current interval
+        bool warp_transparent = !ess;     // no lane of the warp saw a visible sample in the previous round
         while (true) {
             bool have = false;
             if (alive) {
@@ -592,6 +613,7 @@ march_kernel(const __grid_constant__ MarchArgs a) {
                 }
             }
             if (!__any_sync(0xffffffffu, have)) break;
+            bool visible = false;
             if (have) {
                 ++n_fetched;
                 const float fi = (float)i;
@@ -599,7 +621,7 @@ march_kernel(const __grid_constant__ MarchArgs a) {
                 if constexpr (TEX) {
                     // texel centres sit at integer + 0.5 in unnormalised texture space; width = z
                     const float4 t = tex3D<float4>(a.tex, z + 0.5f - (float)ogz, y + 0.5f - (float)ogy, x + 0.5f - (float)ogx);
-                    shade_fast(a, s_lut, t.x, t.y, t.z, t.w, acc);
+                    visible = shade_fast(a, s_lut, t.x, t.y, t.z, t.w, acc);
                 } else {
                     // lower taps floor(x) in [-1, n-1] (the apron holds the clamped texels), upper taps = lower + 1
                     const int ix = __float2int_rd(x), iy = __float2int_rd(y), iz = __float2int_rd(z);
@@ -607,6 +629,22 @@ march_kernel(const __grid_constant__ MarchArgs a) {
                     const IDX e = (IDX)(ix - ogx) * (IDX)vol.pitch_x + (IDX)(iy - ogy) * (IDX)vol.pitch_y + (IDX)(iz - ogz);
                     const char *p00 = a.tap_base + (long long)e * ENTRY_BYTES;
                     const char *p01 = p00 + a.stride_y, *p10 = p00 + a.stride_x, *p11 = p10 + a.stride_y;
+                    // Density first while the warp travels through transparent space (PYVR_DENSITY_FIRST): the 8
+                    // scalars alone (32 of the 128 gather bytes) decide whether the sample is visible; only visible
+                    // samples fetch their texels.  Same arithmetic on the same values as the full path, so the
+                    // skipped samples are exactly the ones that would have added +0.
+                    bool fetch = true;
+#if PYVR_DENSITY_FIRST
+                    if (warp_transparent) {
+                        constexpr int ZOFF = HALF ? 8 : 16;    // texel(iz + 1): the next entry, or the second half of a z-pair
+                        const float d = lerpf(lerpf(lerpf(load_scalar_at<HALF>(p00), load_scalar_at<HALF>(p00 + ZOFF), wz),
+                                                    lerpf(load_scalar_at<HALF>(p01), load_scalar_at<HALF>(p01 + ZOFF), wz), wy),
+                                              lerpf(lerpf(load_scalar_at<HALF>(p10), load_scalar_at<HALF>(p10 + ZOFF), wz),
+                                                    lerpf(load_scalar_at<HALF>(p11), load_scalar_at<HALF>(p11 + ZOFF), wz), wy), wx);
+                        fetch = lut_alpha(a, s_lut, d) != 0.0f;
+                    }
+#endif
+                    if (fetch) {
                     Texel2 c000, c001, c010, c011, c100, c101, c110, c111;
                     load_row<HALF, PAIR>(p00, c000, c001);
                     load_row<HALF, PAIR>(p01, c010, c011);
@@ -630,7 +668,8 @@ march_kernel(const __grid_constant__ MarchArgs a) {
                                   lerp2(lerp2(c100.sn, c101.sn, tz2), lerp2(c110.sn, c111.sn, tz2), ty2), tx2), density, nx);
                     unpack2(lerp2(lerp2(lerp2(c000.yz, c001.yz, tz2), lerp2(c010.yz, c011.yz, tz2), ty2),
                                   lerp2(lerp2(c100.yz, c101.yz, tz2), lerp2(c110.yz, c111.yz, tz2), ty2), tx2), ny, nz);
-                    shade_fast(a, s_lut, density, nx, ny, nz, acc);
+                    visible = shade_fast(a, s_lut, density, nx, ny, nz, acc);
+                    }
                 }
                 if (acc.a >= a.term_alpha) {
                     terminated = i < max_last;
@@ -639,6 +678,9 @@ march_kernel(const __grid_constant__ MarchArgs a) {
                 }
                 ++i;
             }
+#if PYVR_DENSITY_FIRST
+            warp_transparent = !__any_sync(0xffffffffu, visible);
+#endif
         }
         if (hit) n_samples = (unsigned)max(last - i_lo + 1, 0);
     }
