@@ -187,7 +187,7 @@ void fill_volume_desc(pyvr_ctx *c, const int local[3], const int global[3], cons
         const double ext = (double)bmax[a] - (double)bmin[a];
         v.vscale[a] = (float)((double)v.gn[a] / ext);
         v.voff[a] = (float)(-(double)bmin[a] * (double)v.gn[a] / ext - 0.5);
-        v.ncell[a] = (v.n[a] + 7) / 8;
+        v.ncell[a] = (v.n[a] + kCell - 1) / kCell;
     }
     // padded pitches (common.cuh): rows of n[2] + 2 entries, planes of n[1] + 2 rows, rounded up to the residue
     // that rotates the L1 bank of texel (ix, iy, iz) by 3*ix + iy entries.  All 16 residue pairs were measured on

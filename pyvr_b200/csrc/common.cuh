@@ -45,7 +45,7 @@ struct VolumeDesc {
     float bmin[3], bmax[3];
     // fast path: voxel coordinate = world * vscale + voff  (= tc * n - 0.5)
     float vscale[3], voff[3];
-    // empty-space skipping: one byte per 8^3 macrocell (a cell is "active" if some sample in it may have
+    // empty-space skipping: one byte per macrocell (kCell^3 voxels, 8^3 by default) (a cell is "active" if some sample in it may have
     // alpha != 0): b < 128 = inactive and every cell within chessboard radius b-1 is inactive; b >= 128 =
     // active and every cell within radius b-128 is active.  Plus the bounding box of the active cells
     // {lo_x, lo_y, lo_z, hi_x, hi_y, hi_z} in cell units (hi inclusive; lo > hi when no cell is active).
@@ -132,6 +132,12 @@ cudaError_t launch_pack_texels(const float *scalar, const float *normals, const 
 cudaError_t launch_fill_apron(const VolumeDesc &vol, bool half_texels, cudaStream_t stream);
 cudaError_t launch_cell_minmax(const VolumeDesc &vol, bool half_texels, float2 *cell_minmax,
                                cudaStream_t stream);
+// Macrocell edge of the empty-space map: 2^PYVR_CELL_SHIFT voxels.  8 measured against 4 on C3 in round 2
+// (profiles/r02_cell_ab.txt): smaller cells skip ~9 % more samples but the map walk visits more of them.
+#ifndef PYVR_CELL_SHIFT
+#define PYVR_CELL_SHIFT 3
+#endif
+constexpr int kCellShift = PYVR_CELL_SHIFT, kCell = 1 << kCellShift;
 constexpr int kCellDistCap = 15;      // distances saturate here (a nibble); a saturated value is a lower bound
 constexpr int kCellDistSweeps = 14;   // relaxation sweeps: every distance <= 14 is exact
 cudaError_t launch_cell_classify(const float2 *cell_minmax, const VolumeDesc &vol, const float4 *lut,

@@ -493,10 +493,10 @@ march_kernel(const __grid_constant__ MarchArgs a) {
                         j_hi = j_lo - 1;
                     } else {
                         float en = -3.0e38f, exi = 3.0e38f;
-                        const int fx0 = vol.org[0] + 8 * cx0, fy0 = vol.org[1] + 8 * cy0, fz0 = vol.org[2] + 8 * cz0;
-                        index_slab(X0, DX, fx0 == 0 ? -0.5f : (float)fx0, fminf((float)(vol.org[0] + 8 * cx1 + 8), hx), en, exi);
-                        index_slab(Y0, DY, fy0 == 0 ? -0.5f : (float)fy0, fminf((float)(vol.org[1] + 8 * cy1 + 8), hy), en, exi);
-                        index_slab(Z0, DZ, fz0 == 0 ? -0.5f : (float)fz0, fminf((float)(vol.org[2] + 8 * cz1 + 8), hz), en, exi);
+                        const int fx0 = vol.org[0] + kCell * cx0, fy0 = vol.org[1] + kCell * cy0, fz0 = vol.org[2] + kCell * cz0;
+                        index_slab(X0, DX, fx0 == 0 ? -0.5f : (float)fx0, fminf((float)(vol.org[0] + kCell * cx1 + kCell), hx), en, exi);
+                        index_slab(Y0, DY, fy0 == 0 ? -0.5f : (float)fy0, fminf((float)(vol.org[1] + kCell * cy1 + kCell), hy), en, exi);
+                        index_slab(Z0, DZ, fz0 == 0 ? -0.5f : (float)fz0, fminf((float)(vol.org[2] + kCell * cz1 + kCell), hz), en, exi);
                         j_lo = max(j_lo, (int)fminf(fmaxf(floorf(en) - 1.0f, 0.0f), (float)n_steps));
                         j_hi = min(j_hi, (int)fminf(fmaxf(ceilf(exi) + 1.0f, -1.0f), (float)n_steps));
                     }
@@ -540,8 +540,8 @@ march_kernel(const __grid_constant__ MarchArgs a) {
             // a zero direction component counts as "up" with an infinite reciprocal, i.e. it never exits.
             const float rDX = DX != 0.0f ? 1.0f / DX : 3.0e38f, rDY = DY != 0.0f ? 1.0f / DY : 3.0e38f,
                         rDZ = DZ != 0.0f ? 1.0f / DZ : 3.0e38f;
-            const int fstep_x = DX < 0.0f ? -8 : 8, fstep_y = DY < 0.0f ? -8 : 8, fstep_z = DZ < 0.0f ? -8 : 8;
-            const int fbase_x = (DX < 0.0f ? 0 : 8) + ogx, fbase_y = (DY < 0.0f ? 0 : 8) + ogy, fbase_z = (DZ < 0.0f ? 0 : 8) + ogz;
+            const int fstep_x = DX < 0.0f ? -kCell : kCell, fstep_y = DY < 0.0f ? -kCell : kCell, fstep_z = DZ < 0.0f ? -kCell : kCell;
+            const int fbase_x = (DX < 0.0f ? 0 : kCell) + ogx, fbase_y = (DY < 0.0f ? 0 : kCell) + ogy, fbase_z = (DZ < 0.0f ? 0 : kCell) + ogz;
             n_iv = 0; iv_next = 0; walked = true;
             int cs = -1, ce = -1;          // the interval being built
             int k = walk_i;
@@ -554,12 +554,12 @@ march_kernel(const __grid_constant__ MarchArgs a) {
                 const float x = fmaf(fk, DX, X0), y = fmaf(fk, DY, Y0), z = fmaf(fk, DZ, Z0);
                 const int lx = max(__float2int_rd(x), 0) - ogx, ly = max(__float2int_rd(y), 0) - ogy,
                           lz = max(__float2int_rd(z), 0) - ogz;     // lower tap, local to the stored block
-                const int b = __ldg(vol.cell_dist + ((lx >> 3) * vol.ncell[1] + (ly >> 3)) * vol.ncell[2] + (lz >> 3));
+                const int b = __ldg(vol.cell_dist + ((lx >> kCellShift) * vol.ncell[1] + (ly >> kCellShift)) * vol.ncell[2] + (lz >> kCellShift));
                 const bool active = b >= 128;
                 const int r = (b & 127) - (active ? 0 : 1);
-                const float fx = fminf(fmaxf((float)((lx & ~7) + r * fstep_x + fbase_x), -0.5f), hx);
-                const float fy = fminf(fmaxf((float)((ly & ~7) + r * fstep_y + fbase_y), -0.5f), hy);
-                const float fz = fminf(fmaxf((float)((lz & ~7) + r * fstep_z + fbase_z), -0.5f), hz);
+                const float fx = fminf(fmaxf((float)((lx & ~(kCell - 1)) + r * fstep_x + fbase_x), -0.5f), hx);
+                const float fy = fminf(fmaxf((float)((ly & ~(kCell - 1)) + r * fstep_y + fbase_y), -0.5f), hy);
+                const float fz = fminf(fmaxf((float)((lz & ~(kCell - 1)) + r * fstep_z + fbase_z), -0.5f), hz);
                 const float tmin = fminf(fminf((fx - x) * rDX, (fy - y) * rDY), (fz - z) * rDZ);
                 const int stay = min(max(__float2int_rd(tmin - 0.01f), 1), 1 << 24);
                 if (active) {

@@ -104,9 +104,9 @@ cell_minmax_kernel(VolumeDesc v, float2 *__restrict__ out) {
         const int cz = (int)(cell % v.ncell[2]);
         const long long r = cell / v.ncell[2];
         const int cy = (int)(r % v.ncell[1]), cx = (int)(r / v.ncell[1]);
-        const int x0 = 8 * cx, y0 = 8 * cy, z0 = 8 * cz;
-        const int wx = min(x0 + 8, v.n[0] - 1) - x0 + 1, wy = min(y0 + 8, v.n[1] - 1) - y0 + 1,
-                  wz = min(z0 + 8, v.n[2] - 1) - z0 + 1;
+        const int x0 = kCell * cx, y0 = kCell * cy, z0 = kCell * cz;
+        const int wx = min(x0 + kCell, v.n[0] - 1) - x0 + 1, wy = min(y0 + kCell, v.n[1] - 1) - y0 + 1,
+                  wz = min(z0 + kCell, v.n[2] - 1) - z0 + 1;
         float lo = INFINITY, hi = -INFINITY;
         for (int t = lane; t < wx * wy * wz; t += 32) {
             const int dz = t % wz, dy = (t / wz) % wy, dx = t / (wz * wy);

@@ -15,6 +15,7 @@ print('$tag: value=%.1f Gs/s ms/view=%.3f normals_ms=%s' % (d['value'], r['kerne
 one "default ess" X=0 --
 one "nodf ess" PYVR_CUDA_LIB=$PWD/pyvr_b200/libpyvr_cuda_nodf.so --
 one "mb8 ess" PYVR_CUDA_LIB=$PWD/pyvr_b200/libpyvr_cuda_mb8.so --
+one "cell4 ess" PYVR_CUDA_LIB=$PWD/pyvr_b200/libpyvr_cuda_cell4.so --
 one "default dense" X=0 -- --no-ess
 one "nodf dense" PYVR_CUDA_LIB=$PWD/pyvr_b200/libpyvr_cuda_nodf.so -- --no-ess
 one "default f16 ess" X=0 -- --texels f16
@@ -29,6 +30,14 @@ r=d['roofline']
 print('value %.1f e2e %.1f fps %.1f timed %.2fs launches %d' % (d['value'], d['e2e']['value'], d['frames_per_s'], d['timed_region_s'], d['gpu_launches']))
 print('roofline: achieved %.0f peak(L1 measured) %.0f frac %.3f nominal %.0f | l2 peak %.0f | hbm %s' % (r['achieved'], r['peak'], r['frac'], r['peak_nominal'], r['l2']['peak'], r['hbm']))
 print('dense', r['dense']); print('alts', d['alternatives']); print('normals', d['normals_kernel']); print('cpu', d.get('cpu_baseline'))
+PY
+timeout 600 python bench.py --workload c4 --steps 5 --warmup 2 > $OUT/r02f_c4_1gpu.json 2> $OUT/r02f_c4_1gpu.err; python - <<'PY'
+import json
+try:
+    d=json.loads(open('gpurun_out/r02f_c4_1gpu.json').read().strip().splitlines()[-1])
+    print('C4 1 GPU: %.2f ms/frame  %.1f Gsamples/s  march share %.2f' % (d['ms_per_step'], d['value'], d['roofline']['march_share_of_step']))
+except Exception as e:
+    print('C4 failed', e, open('gpurun_out/r02f_c4_1gpu.err').read()[-600:])
 PY
 for cfg in "march::" "march_dense::--no-ess"; do
   IFS=: read tag env flags <<< "$cfg"
