@@ -252,7 +252,9 @@ class PeerFlags:
 
         self._cabi, self.device, self.slots = _cabi, device, int(slots)
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
-        self.own = _cabi.DeviceBuffer(self.slots * self.world * 4, device)
+        # 2 MiB: a whole allocation of its own (an IPC handle names the underlying allocation, and the driver packs
+        # small cudaMalloc blocks into shared pages)
+        self.own = _cabi.DeviceBuffer(max(self.slots * self.world * 4, 2 << 20), device)
         self.own.from_host(np.zeros(self.slots * self.world, np.uint32))
         handles = [None] * self.world
         dist.all_gather_object(handles, self.own.ipc_handle(), group=group)
