@@ -276,16 +276,18 @@ def _dist_worker(rank, world, port, out_dir, exchange):
         cam, cfg = Camera.isometric_view(distance=3.0), RenderConfig.balanced()
         position, _ = cam.get_camera_vectors()
         b = mg.brick_of_rank(data.shape, rank, world)
-        session = mg.SortLastSession(data.shape, vol.min_bounds, vol.max_bounds, W * H, device=rank, exchange=exchange)
         with VolumeRenderer(W, H, config=cfg, light=light, device=rank) as r:
-            r.load_brick(vol.data[b.slices()], vol.normals[b.slices()], data.shape, b.origin, b.own_lo, b.own_hi,
-                         vol.min_bounds, vol.max_bounds)
+            # the session binds the renderer to torch's current stream (merges, flags and NCCL traffic run there)
+            session = mg.SortLastSession(data.shape, vol.min_bounds, vol.max_bounds, W * H, device=rank, exchange=exchange,
+                                         renderer=r)
+            # the brick's normals from its own voxels + a one-voxel halo, not from the whole normal volume
+            r.load_brick(vol.data[b.slices()], mg.brick_normals(vol.data, b, device=rank), data.shape, b.origin, b.own_lo,
+                         b.own_hi, vol.min_bounds, vol.max_bounds)
             r.set_camera(cam)
             r.set_lut(lut)
-            r.set_stream(torch.cuda.current_stream().cuda_stream)
-            for _ in range(2):   # twice: buffers are reused across frames
+            for it in range(3):   # several frames: buffers and peer flags are reused; the last one fuses finalize into the merge
                 r.render_accum_to_device(session.image_ptr())
-                piece_range, piece = session.composite(position)
+                piece_range, piece = session.composite(position, finalize_to=0 if (exchange == "p2p" and it == 2) else None)
                 frame = session.gather_rgba8(piece_range, piece)
                 if isinstance(frame, int):      # p2p: raw pointer of the IPC-shared frame buffer on rank 0
                     torch.cuda.synchronize()
@@ -305,9 +307,20 @@ def _dist_worker(rank, world, port, out_dir, exchange):
             tiles = torch.zeros(H * W * 4, dtype=torch.uint8, device="cuda")
             r.render_to_device(tiles.data_ptr())
             mg.reduce_tile_frames(tiles, dst=0)
+            # ... and fused: every rank's march stores its pixels straight into rank 0's frame (peer memory + flags)
+            ts = mg.TileSession(r, W * H, device=rank)
+            for _ in range(3):
+                ptr = ts.render()
+                if ptr is not None:
+                    torch.cuda.synchronize()
+                    fused = np.empty(W * H * 4, np.uint8)
+                    _cabi.check(_cabi.lib().pyvr_cuda_memcpy(rank, fused.ctypes.data, ctypes.c_void_p(ptr), W * H * 4, 2, None))
+                ts.release()
+            ts.close()
         if rank == 0:
             np.save(os.path.join(out_dir, "frame.npy"), frame.cpu().numpy().reshape(H, W, 4))
             np.save(os.path.join(out_dir, "tiles.npy"), tiles.cpu().numpy().reshape(H, W, 4))
+            np.save(os.path.join(out_dir, "tiles_fused.npy"), fused.reshape(H, W, 4))
             np.save(os.path.join(out_dir, "samples.npy"), samples.cpu().numpy())
         session.close()
     finally:
@@ -337,4 +350,5 @@ def test_sort_last_and_tiles_across_processes(scene, tmp_path, exchange):
     m = image_metrics(got, want)
     assert m["max_abs"] <= 3 and m["frac_within_1"] >= 0.999, m
     assert np.array_equal(np.load(tmp_path / "tiles.npy"), want)
+    assert np.array_equal(np.load(tmp_path / "tiles_fused.npy"), want)
     assert np.array_equal(np.load(tmp_path / "relay.npy"), want)
