@@ -290,7 +290,7 @@ __device__ __forceinline__ void index_slab(float X0, float D, float lo, float hi
 #define PYVR_LANE_ARR 1     // measured on C3 (profiles/r02_lane_ab.txt): 4x2 blocks 477, 2x4 blocks 448-470, rows 449 Gsamples/s
 #endif
 #ifndef PYVR_DENSITY_FIRST
-#define PYVR_DENSITY_FIRST 1
+#define PYVR_DENSITY_FIRST 0   // measured (profiles/r02_density_first_ab.txt): 452 vs 482 Gsamples/s with ESS, 122 vs 130 dense
 #endif
 #ifndef PYVR_PF_DIST
 #define PYVR_PF_DIST 0     // samples ahead to prefetch (0 = off); PYVR_PF_LEVEL 1 = L1, 2 = L2
@@ -306,7 +306,10 @@ __device__ __forceinline__ void prefetch_line(const char *p) {
 #endif
 }
 
-constexpr int MAX_IV = 6;   // active-interval table entries per ray (shared memory); refilled when exhausted
+#ifndef PYVR_MAX_IV
+#define PYVR_MAX_IV 6
+#endif
+constexpr int MAX_IV = PYVR_MAX_IV;   // active-interval table entries per ray (shared memory); refilled when exhausted
 
 #ifndef PYVR_MARCH_MIN_BLOCKS
 #define PYVR_MARCH_MIN_BLOCKS 7   // 7 CTAs x 4 warps per SM <=> at most 72 registers per thread
@@ -629,10 +632,13 @@ march_kernel(const __grid_constant__ MarchArgs a) {
                     const IDX e = (IDX)(ix - ogx) * (IDX)vol.pitch_x + (IDX)(iy - ogy) * (IDX)vol.pitch_y + (IDX)(iz - ogz);
                     const char *p00 = a.tap_base + (long long)e * ENTRY_BYTES;
                     const char *p01 = p00 + a.stride_y, *p10 = p00 + a.stride_x, *p11 = p10 + a.stride_y;
-                    // Density first while the warp travels through transparent space (PYVR_DENSITY_FIRST): the 8
+                    // Density first while the warp travels through transparent space (PYVR_DENSITY_FIRST, off): the 8
                     // scalars alone (32 of the 128 gather bytes) decide whether the sample is visible; only visible
                     // samples fetch their texels.  Same arithmetic on the same values as the full path, so the
-                    // skipped samples are exactly the ones that would have added +0.
+                    // skipped samples are exactly the ones that would have added +0.  A NEGATIVE result on the B200:
+                    // eight 4-byte gathers cost the L1 data stage about as much as the four 32-byte ones they
+                    // replace (the stage is paid per quarter-warp pass, not per byte), so even the dense march,
+                    // where 79 % of the samples are transparent, got 6 % slower.
                     bool fetch = true;
 #if PYVR_DENSITY_FIRST
                     if (warp_transparent) {
