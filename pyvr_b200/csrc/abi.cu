@@ -330,6 +330,7 @@ MarchArgs make_args(const pyvr_ctx *c) {
     a.shard_rank = c->shard_rank;
     a.shard_count = c->shard_count;
     a.shard_shift = c->shard_shift;
+    a.tile_counter = reinterpret_cast<unsigned *>(c->d_counters + CNT_N);
     return a;
 }
 
@@ -421,7 +422,7 @@ int pyvr_cuda_create(int device, int width, int height, pyvr_ctx **out_ctx) {
     cudaError_t e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMalloc(&c->frames, frame_pixels(c) * sizeof(uchar4) * kRing * kSlotViews);
-    if (e == cudaSuccess) e = cudaMalloc(&c->d_counters, sizeof(unsigned long long) * CNT_N);
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_counters, sizeof(unsigned long long) * (CNT_N + 1));   // + tile-queue ticket
     if (e == cudaSuccess) e = cudaMallocHost(&c->h_counters, sizeof(unsigned long long) * CNT_N);
     for (int i = 0; i < kRing && e == cudaSuccess; ++i) {
         e = cudaEventCreateWithFlags(&c->slot_rendered[i], cudaEventDisableTiming);

@@ -91,6 +91,8 @@ struct MarchArgs {
     // shard_rank only and leaves every other pixel untouched (the C ABI clears the frame first unless the caller
     // asked for in-place sharding into a frame that all ranks write).  shard_count <= 1: everything.
     int shard_rank, shard_count, shard_shift;
+    int n_views;                   // views of this launch (filled by the launcher)
+    unsigned *tile_counter;        // PYVR_PERSISTENT builds: ticket counter of the tile queue (zeroed per launch)
 };
 
 // Fragment colour -> what fbo.read returns: clamp to [0,1], blend SRC_ALPHA / ONE_MINUS_SRC_ALPHA onto the

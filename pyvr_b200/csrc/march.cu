@@ -286,6 +286,9 @@ __device__ __forceinline__ void index_slab(float X0, float D, float lo, float hi
     }
 }
 
+#ifndef PYVR_PERSISTENT
+#define PYVR_PERSISTENT 0   // 1: one wave of CTAs, warps pull tiles off an atomic queue (not with image-space sharding)
+#endif
 #ifndef PYVR_LANE_ARR
 #define PYVR_LANE_ARR 1     // measured on C3 (profiles/r02_lane_ab.txt): 4x2 blocks 477, 2x4 blocks 448-470, rows 449 Gsamples/s
 #endif
@@ -293,7 +296,7 @@ __device__ __forceinline__ void index_slab(float X0, float D, float lo, float hi
 #define PYVR_DENSITY_FIRST 0   // measured (profiles/r02_density_first_ab.txt): 452 vs 482 Gsamples/s with ESS, 122 vs 130 dense
 #endif
 #ifndef PYVR_PF_DIST
-#define PYVR_PF_DIST 0     // samples ahead to prefetch (0 = off); PYVR_PF_LEVEL 1 = L1, 2 = L2
+#define PYVR_PF_DIST 0      // samples ahead to prefetch (0 = off); PYVR_PF_LEVEL 1 = L1, 2 = L2
 #endif
 #ifndef PYVR_PF_LEVEL
 #define PYVR_PF_LEVEL 2
@@ -335,9 +338,36 @@ march_kernel(const __grid_constant__ MarchArgs a) {
     const int lane_x = (lane & 3) + 4 * ((lane >> 3) & 1), lane_y = ((lane >> 2) & 1) + 2 * (lane >> 4);
 #elif PYVR_LANE_ARR == 2    // quarter-warp = 2x4 pixel block
     const int lane_x = (lane & 1) + 2 * (lane >> 3), lane_y = (lane >> 1) & 3;
+#elif PYVR_LANE_ARR == 3    // 4 consecutive lanes (one LDG.256 data-stage pass) = 2x2 pixels, quarter-warp = 4x2
+    const int lane_x = (lane & 1) + 2 * ((lane >> 2) & 1) + 4 * ((lane >> 3) & 1), lane_y = ((lane >> 1) & 1) + 2 * (lane >> 4);
+#elif PYVR_LANE_ARR == 4    // 4 consecutive lanes = 2x2 pixels, quarter-warp = 2x4
+    const int lane_x = (lane & 1) + 2 * (lane >> 3), lane_y = ((lane >> 1) & 1) + 2 * ((lane >> 2) & 1);
 #else                       // quarter-warp = one 8-pixel row
     const int lane_x = lane % WARP_W, lane_y = lane / WARP_W;
 #endif
+    extern __shared__ float4 s_lut[];
+    stage_lut(s_lut, a.lut, a.lut_size, CTA_THREADS);
+    __syncthreads();
+    const VolumeDesc &vol = a.vol;
+    __shared__ int s_iv[2 * MAX_IV][CTA_THREADS];   // per-ray table of active index intervals, see the pre-walk below
+
+#if PYVR_PERSISTENT
+    // Persistent warps with an atomic tile queue: the grid is one wave of CTAs, every
+    // WARP pulls 8x4-pixel tiles off a global counter until none is left.  Consecutive tickets are the four warp
+    // tiles of one 16x8 CTA tile, then the next CTA tile along the image row, so warps that run together still
+    // share lines.  No warp waits for the slowest warp of its CTA and the LUT is staged once per SM slot.
+    const unsigned tiles_cx = (unsigned)((a.width + TILE_W - 1) / TILE_W), tiles_cy = (unsigned)((a.height + TILE_H - 1) / TILE_H);
+    const unsigned total_tickets = tiles_cx * tiles_cy * (unsigned)(CTA_WX * CTA_WY) * (unsigned)a.n_views;
+    for (;;) {
+    unsigned ticket = 0;
+    if (lane == 0) ticket = atomicAdd(a.tile_counter, 1u);
+    ticket = __shfl_sync(0xffffffffu, ticket, 0);
+    if (ticket >= total_tickets) break;
+    const int wsub = (int)(ticket % (unsigned)(CTA_WX * CTA_WY));
+    const unsigned cta_tile = ticket / (unsigned)(CTA_WX * CTA_WY);
+    const int tile_x = (int)(cta_tile % tiles_cx), tile_y = (int)((cta_tile / tiles_cx) % tiles_cy);
+    const int view_index = (int)(cta_tile / (tiles_cx * tiles_cy));
+#else
     // image-space sharding (multi-GPU tiles): groups of 2^shift x 2^shift CTA tiles are dealt over the ranks along
     // image rows, every row of groups shifted by one rank against the one below: owner(gx, gy) = (gx + gy) mod P.
     // Only the owned tiles are launched: blockIdx.x enumerates this rank's groups of the row.
@@ -348,15 +378,13 @@ march_kernel(const __grid_constant__ MarchArgs a) {
         tile_x = ((first + k * a.shard_count) << sh) + (blockIdx.x & ((1 << sh) - 1));
         if (tile_x * TILE_W >= a.width) return;
     }
-    const int px = tile_x * TILE_W + (warp % CTA_WX) * WARP_W + lane_x;
-    const int py = blockIdx.y * TILE_H + (warp / CTA_WX) * WARP_H + lane_y;
+    const int tile_y = blockIdx.y, view_index = blockIdx.z, wsub = warp;
+    {
+#endif
+    const int px = tile_x * TILE_W + (wsub % CTA_WX) * WARP_W + lane_x;
+    const int py = tile_y * TILE_H + (wsub / CTA_WX) * WARP_H + lane_y;
     const bool in_image = px < a.width && py < a.height;
-
-    extern __shared__ float4 s_lut[];
-    stage_lut(s_lut, a.lut, a.lut_size, CTA_THREADS);
-    __syncthreads();
-    const pyvr_view &vw = a.views[blockIdx.z];
-    const VolumeDesc &vol = a.vol;
+    const pyvr_view &vw = a.views[view_index];
 
     Accum acc = {0.0f, 0.0f, 0.0f, 0.0f};
     unsigned n_samples = 0, n_fetched = 0;
@@ -515,7 +543,7 @@ march_kernel(const __grid_constant__ MarchArgs a) {
         // relay: continue the accumulation of the bricks in front.  A ray that arrives saturated executes no
         // sample here, exactly as the single pass would not (volume.frag.glsl:87 tests before each sample).
         if (a.in_acc != nullptr && in_image) {
-            const float4 in = a.in_acc[((size_t)blockIdx.z * a.height + py) * a.width + px];
+            const float4 in = a.in_acc[((size_t)view_index * a.height + py) * a.width + px];
             acc.r = in.x; acc.g = in.y; acc.b = in.z; acc.a = in.w;
             if (acc.a >= a.term_alpha) { alive = false; last = i_lo - 1; }
         }
@@ -530,7 +558,7 @@ march_kernel(const __grid_constant__ MarchArgs a) {
         const float hx = (float)vol.gn[0] - 0.5f, hy = (float)vol.gn[1] - 0.5f, hz = (float)vol.gn[2] - 0.5f;
         const int ogx = BRICK ? vol.org[0] : 0, ogy = BRICK ? vol.org[1] : 0, ogz = BRICK ? vol.org[2] : 0;
         const int max_last = a.max_steps - 1;
-        __shared__ int s_iv[2 * MAX_IV][CTA_THREADS];   // [2k] = first index, [2k+1] = last index of interval k
+        // s_iv[2k] = first index, s_iv[2k+1] = last index of interval k
         int n_iv = 0, iv_next = 0;
         int walk_i = i;            // where the walk resumes when the table has been consumed
         bool walked = true;        // the walk has reached j_hi
@@ -657,13 +685,21 @@ march_kernel(const __grid_constant__ MarchArgs a) {
                     load_row<HALF, PAIR>(p10, c100, c101);
                     load_row<HALF, PAIR>(p11, c110, c111);
 #if PYVR_PF_DIST > 0
-                    if (i + PYVR_PF_DIST < run_end) {   // warm the lines of a later sample of this interval
+                    if (i + PYVR_PF_DIST < run_end) {
+                        // A/B builds only: ask L2 for the four corner rows of the sample PYVR_PF_DIST steps ahead (the
+                        // lattice makes its address known now).  A NEGATIVE result on both regimes
+                        // (profiles/r02_c4_prefetch_ab.txt): C3 477 -> 398 Gsamples/s (prefetches take data-stage slots
+                        // too), C4 8.7 -> 16-19 ms per frame (sparse rays: DRAM is already the bound and the extra
+                        // sectors are evicted before use).  As a run-time option the branch also cost the f16 kernel
+                        // 80 bytes of spills inside the loop, so it is compile-time only.
                         const float fp = fi + (float)PYVR_PF_DIST;
                         const int jx = __float2int_rd(fmaf(fp, DX, X0)), jy = __float2int_rd(fmaf(fp, DY, Y0)),
                                   jz = __float2int_rd(fmaf(fp, DZ, Z0));
                         const IDX ep = (IDX)(jx - ogx) * (IDX)vol.pitch_x + (IDX)(jy - ogy) * (IDX)vol.pitch_y + (IDX)(jz - ogz);
                         const char *q = a.tap_base + (long long)ep * ENTRY_BYTES;
                         prefetch_line(q);
+                        prefetch_line(q + a.stride_y);
+                        prefetch_line(q + a.stride_x);
                         prefetch_line(q + a.stride_x + a.stride_y);
                     }
 #endif
@@ -693,7 +729,7 @@ march_kernel(const __grid_constant__ MarchArgs a) {
 
     // fragment colour -> [0,1] clamp -> blend onto the (0,0,0,0) clear -> clamp -> round to RGBA8
     if (in_image) {
-        const size_t pix = ((size_t)blockIdx.z * a.height + py) * a.width + px;
+        const size_t pix = ((size_t)view_index * a.height + py) * a.width + px;
         if (a.out_acc) a.out_acc[pix] = make_float4(acc.r, acc.g, acc.b, acc.a);
         if (a.out8) a.out8[pix] = fragment_to_rgba8(acc.r, acc.g, acc.b, acc.a, a.flags);
     }
@@ -714,6 +750,7 @@ march_kernel(const __grid_constant__ MarchArgs a) {
             if (t) atomicAdd(a.counters + CNT_TERM, (unsigned long long)t);
         }
     }
+    }   // one tile (PYVR_PERSISTENT: next ticket)
 }
 
 template <bool STRICT, bool HALF, typename IDX, bool BRICK, bool PAIR, bool TEX = false>
@@ -738,7 +775,24 @@ cudaError_t launch_one(const MarchArgs &a, int n_views, cudaStream_t stream) {
         tiles_x = ((groups_x + a.shard_count - 1) / a.shard_count) * group;
     }
     dim3 grid(tiles_x, (a.height + TILE_H - 1) / TILE_H, n_views);
-    kern<<<grid, CTA_THREADS, smem, stream>>>(a);
+#if PYVR_PERSISTENT
+    if (a.shard_count <= 1 && a.tile_counter != nullptr) {
+        static int slots = 0;       // resident CTAs of this instantiation on the whole device
+        if (slots == 0) {
+            int per_sm = 0, sms = 0, dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, CTA_THREADS, smem);
+            slots = (per_sm > 0 ? per_sm : 1) * (sms > 0 ? sms : 1);
+        }
+        cudaError_t e = cudaMemsetAsync(a.tile_counter, 0, sizeof(unsigned), stream);
+        if (e != cudaSuccess) return e;
+        grid = dim3(slots, 1, 1);
+    }
+#endif
+    MarchArgs b = a;
+    b.n_views = n_views;
+    kern<<<grid, CTA_THREADS, smem, stream>>>(b);
     return cudaGetLastError();
 }
 
