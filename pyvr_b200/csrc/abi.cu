@@ -74,6 +74,8 @@ struct pyvr_ctx {
     bool shard_in_place = false;           // true: foreign pixels are left untouched (all ranks write one shared frame)
     int pair_option = -1;   // z-pair entries: -1 auto (when the doubled array stays under kPairBudget), 0 off, 1 on
     bool use_pair = false;  // decided per upload
+    int brick8_option = 0;  // 2x2x2-texel bricks (common.cuh): 0 off (default: slower, see choose_layout), 1 on
+    bool use_brick8 = false;
     cudaArray_t tex_array = nullptr;        // PYVR_FLAG_HWTEX: built on first use from the packed texels
     cudaTextureObject_t tex_obj = 0;
 
@@ -162,19 +164,28 @@ void inverse4_f32(const float *m, float *o) {
     o[15] = (a20 * b03 - a21 * b01 + a22 * b00) * id;
 }
 
-// z-pair layout (common.cuh) for this upload?
-void choose_pair(pyvr_ctx *c, const int local[3]) {
+// Layout (common.cuh) for this upload: rows, z-paired if memory allows, or -- option "brick8" -- 2x2x2-texel bricks.
+// Bricks are a measured NEGATIVE result and therefore off unless asked for (profiles/r02_brick8_ab.txt, C4 = 2048^3
+// f16x4 at 2160p, rays 1.2-1.6 voxels apart): they cut the DRAM traffic of a frame from 45.3 GB to 18.9 GB (ncu) and
+// halve the memory, yet the frame takes 9.3-10.1 ms instead of 8.0-8.6 ms.  The row march is DRAM-bound (5.3 TB/s, 65 %
+// busy); the brick march is bound by the L1 misses an SM can keep in flight -- eight 8-byte requests per sample
+// instead of four 16-byte ones, 43 warp-cycles of long-scoreboard stall per issued instruction, DRAM 25 % busy -- and
+// neither more warps (11 CTAs/SM: 9.9 ms) nor L2 / L1 prefetch of the next bricks (11.2-11.5 ms) fills that gap.
+// On C3 (rays 0.6 voxels apart, L1-bound) bricks cost nothing for f32x4 (478 vs 475 Gsamples/s) and 17 % for f16x4.
+void choose_layout(pyvr_ctx *c, const int local[3]) {
+    c->use_brick8 = c->brick8_option > 0;
     const size_t doubled = (size_t)local[0] * local[1] * local[2] * (c->half_texels ? 8 : 16) * 2;
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) free_b = 0;   // called after the old volume was freed
-    c->use_pair = c->pair_option < 0 ? (double)doubled <= kPairBudget * (double)free_b : c->pair_option != 0;
+    c->use_pair = !c->use_brick8 &&
+                  (c->pair_option < 0 ? (double)doubled <= kPairBudget * (double)free_b : c->pair_option != 0);
 }
 
 // local[3] = stored texel counts along world x, y, z; global/org/own_* = NULL for a whole volume.
 void fill_volume_desc(pyvr_ctx *c, const int local[3], const int global[3], const int org[3],
                       const int own_lo[3], const int own_hi[3], const float bmin[3], const float bmax[3]) {
     VolumeDesc &v = c->vol;
-    choose_pair(c, local);
+    choose_layout(c, local);
     v.bricked = global != nullptr;
     for (int a = 0; a < 3; ++a) {
         v.n[a] = local[a];
@@ -195,6 +206,12 @@ void fill_volume_desc(pyvr_ctx *c, const int local[3], const int global[3], cons
     // round-1 slot swizzle -- 428, (3,1) 449; what matters is that the texels one quarter-warp touches -- a short
     // run along the image-row direction -- spread over the banks.
     v.pair = c->use_pair ? 1 : 0;
+    v.brick8 = c->use_brick8 ? 1 : 0;
+    if (v.brick8) {   // pitches count bricks; the apron is part of the bricked array
+        v.pitch_y = (v.n[2] + 3) >> 1;
+        v.pitch_x = (long long)((v.n[1] + 3) >> 1) * v.pitch_y;
+        return;
+    }
     const int slots = 128 / entry_bytes(c->half_texels, v.pair);
     int rx = 3, ry = 1;
     if (!c->swizzle) rx = ry = 0;
@@ -305,9 +322,15 @@ MarchArgs make_args(const pyvr_ctx *c) {
     MarchArgs a{};
     a.vol = c->vol;
     const long long eb = entry_bytes(c->half_texels, c->vol.pair);
-    a.tap_base = static_cast<const char *>(c->vol.texels) + texel_index(c->vol, 0, 0, 0) * eb;
-    a.stride_y = (long long)c->vol.pitch_y * eb;
-    a.stride_x = c->vol.pitch_x * eb;
+    if (c->vol.brick8) {   // bytes per z-row / x-plane of 8-texel bricks, from the allocation start
+        a.tap_base = static_cast<const char *>(c->vol.texels);
+        a.stride_y = (long long)c->vol.pitch_y * eb * 8;
+        a.stride_x = c->vol.pitch_x * eb * 8;
+    } else {
+        a.tap_base = static_cast<const char *>(c->vol.texels) + texel_index(c->vol, 0, 0, 0) * eb;
+        a.stride_y = (long long)c->vol.pitch_y * eb;
+        a.stride_x = c->vol.pitch_x * eb;
+    }
     a.lut = c->lut;
     a.lut_size = c->lut_size;
     a.width = c->width;
@@ -413,6 +436,8 @@ int pyvr_cuda_create(int device, int width, int height, pyvr_ctx **out_ctx) {
     if (layout) c->swizzle = strcmp(layout, "linear") != 0;   // "linear" = no swizzle, anything else = default
     const char *pair = getenv("PYVR_CUDA_PAIR");
     if (pair) c->pair_option = atoi(pair);
+    const char *b8 = getenv("PYVR_CUDA_BRICK8");
+    if (b8) c->brick8_option = atoi(b8);
     // defaults of the reference renderer: balanced preset, Light.default(), bounds +-0.5
     c->params.step_size = 0.01f; c->params.max_steps = 500; c->params.reference_step_size = 0.01f;
     c->params.ambient = 0.2f; c->params.diffuse = 0.8f;
@@ -483,6 +508,10 @@ int pyvr_cuda_set_option(pyvr_ctx *c, const char *key, int value) {
     if (!c || !key) return fail(PYVR_ERR_INVALID, "ctx or key is NULL");
     if (strcmp(key, "pair") == 0) {   // takes effect at the next upload
         c->pair_option = value < 0 ? -1 : (value != 0);
+        return PYVR_OK;
+    }
+    if (strcmp(key, "brick8") == 0) {   // 2x2x2-texel bricks (0 off, 1 on); takes effect at the next upload
+        c->brick8_option = value > 0;
         return PYVR_OK;
     }
     if (strcmp(key, "shard_shift") == 0) {      // tile-group edge of the image-space sharding, in CTA tiles (log2)

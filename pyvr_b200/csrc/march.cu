@@ -124,6 +124,17 @@ __device__ __forceinline__ void load_row(const char *p, Texel2 &lo, Texel2 &hi) 
     }
 }
 
+// One texel (brick8 layout): LDG.64 (f16x4) or LDG.128 (f32x4).
+template <bool HALF>
+__device__ __forceinline__ void load_one(const char *p, Texel2 &t) {
+    if constexpr (HALF) {
+        const uint2 raw = __ldg(reinterpret_cast<const uint2 *>(p));
+        t.sn = half2_to_f32x2(raw.x); t.yz = half2_to_f32x2(raw.y);
+    } else {
+        asm("ld.global.nc.v2.b64 {%0, %1}, [%2];" : "=l"(t.sn), "=l"(t.yz) : "l"(p));
+    }
+}
+
 // STRICT path: one texel by index (clamped taps, never the apron), unpacked.
 template <bool HALF>
 __device__ __forceinline__ float4 load_texel(const VolumeDesc &v, int ix, int iy, int iz) {
@@ -301,6 +312,9 @@ __device__ __forceinline__ void index_slab(float X0, float D, float lo, float hi
 #ifndef PYVR_PF_LEVEL
 #define PYVR_PF_LEVEL 2
 #endif
+#ifndef PYVR_B8_PF_DIST
+#define PYVR_B8_PF_DIST 0   // brick8 layout: prefetch the bricks of the sample this many steps ahead (0 = off)
+#endif
 __device__ __forceinline__ void prefetch_line(const char *p) {
 #if PYVR_PF_LEVEL == 1
     asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
@@ -326,10 +340,12 @@ constexpr int MAX_IV = PYVR_MAX_IV;   // active-interval table entries per ray (
                                        // 48 warps per SM (measured: 7 -> 699, 10 -> 890, 12 -> 939, 14 -> 583 Gsamples/s on C3)
 #endif
 
-template <bool STRICT, bool HALF, typename IDX, bool BRICK, bool PAIR, bool TEX>
+// LAYOUT: 0 = rows, 1 = rows of z-pair entries, 2 = 2x2x2-texel bricks (common.cuh)
+template <bool STRICT, bool HALF, typename IDX, bool BRICK, int LAYOUT, bool TEX>
 __global__ void __launch_bounds__(CTA_THREADS, TEX ? PYVR_MARCH_MIN_BLOCKS_TEX : (HALF && !STRICT) ? PYVR_MARCH_MIN_BLOCKS_F16 : PYVR_MARCH_MIN_BLOCKS)
 march_kernel(const __grid_constant__ MarchArgs a) {
-    constexpr int ENTRY_BYTES = (HALF ? 8 : 16) << (PAIR ? 1 : 0);
+    constexpr bool PAIR = LAYOUT == 1;
+    constexpr int TEXEL_BYTES = HALF ? 8 : 16, ENTRY_BYTES = TEXEL_BYTES << (PAIR ? 1 : 0);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // lane -> pixel inside the warp's 8x4 tile.  The L1 data stage serves a warp-wide load quarter-warp by
     // quarter-warp (lanes 8q .. 8q+7); how many distinct entries those 8 lanes touch, and on which banks, decides
@@ -558,6 +574,8 @@ march_kernel(const __grid_constant__ MarchArgs a) {
         const float hx = (float)vol.gn[0] - 0.5f, hy = (float)vol.gn[1] - 0.5f, hz = (float)vol.gn[2] - 0.5f;
         const int ogx = BRICK ? vol.org[0] : 0, ogy = BRICK ? vol.org[1] : 0, ogz = BRICK ? vol.org[2] : 0;
         const int max_last = a.max_steps - 1;
+        const IDX PX8 = (IDX)(vol.pitch_x * 8), PY8 = (IDX)vol.pitch_y * 8;   // brick8: texels per x-plane / z-row of bricks
+        (void)PX8; (void)PY8;
         // s_iv[2k] = first index, s_iv[2k+1] = last index of interval k
         int n_iv = 0, iv_next = 0;
         int walk_i = i;            // where the walk resumes when the table has been consumed
@@ -657,6 +675,42 @@ march_kernel(const __grid_constant__ MarchArgs a) {
                     // lower taps floor(x) in [-1, n-1] (the apron holds the clamped texels), upper taps = lower + 1
                     const int ix = __float2int_rd(x), iy = __float2int_rd(y), iz = __float2int_rd(z);
                     const float wx = x - (float)ix, wy = y - (float)iy, wz = z - (float)iz;
+                    Texel2 c000, c001, c010, c011, c100, c101, c110, c111;
+                    bool fetch = true;
+                    if constexpr (LAYOUT == 2) {
+                        // 2x2x2-texel bricks: per axis the brick term and the in-brick bit of the lower and the upper tap
+                        // (coordinates shifted by the apron), then eight single-texel loads.
+                        const int X = ix - ogx + 1, Y = iy - ogy + 1, Z = iz - ogz + 1;
+                        const IDX ex0 = (IDX)(X >> 1) * PX8 + (IDX)((X & 1) << 2), ex1 = (IDX)((X + 1) >> 1) * PX8 + (IDX)(((X + 1) & 1) << 2);
+                        const IDX ey0 = (IDX)(Y >> 1) * PY8 + (IDX)((Y & 1) << 1), ey1 = (IDX)((Y + 1) >> 1) * PY8 + (IDX)(((Y + 1) & 1) << 1);
+                        const IDX ez0 = (IDX)((Z >> 1) << 3) + (IDX)(Z & 1), ez1 = (IDX)(((Z + 1) >> 1) << 3) + (IDX)((Z + 1) & 1);
+                        const IDX e00 = ex0 + ey0, e01 = ex0 + ey1, e10 = ex1 + ey0, e11 = ex1 + ey1;
+                        load_one<HALF>(a.tap_base + (long long)(e00 + ez0) * TEXEL_BYTES, c000);
+                        load_one<HALF>(a.tap_base + (long long)(e00 + ez1) * TEXEL_BYTES, c001);
+                        load_one<HALF>(a.tap_base + (long long)(e01 + ez0) * TEXEL_BYTES, c010);
+                        load_one<HALF>(a.tap_base + (long long)(e01 + ez1) * TEXEL_BYTES, c011);
+                        load_one<HALF>(a.tap_base + (long long)(e10 + ez0) * TEXEL_BYTES, c100);
+                        load_one<HALF>(a.tap_base + (long long)(e10 + ez1) * TEXEL_BYTES, c101);
+                        load_one<HALF>(a.tap_base + (long long)(e11 + ez0) * TEXEL_BYTES, c110);
+                        load_one<HALF>(a.tap_base + (long long)(e11 + ez1) * TEXEL_BYTES, c111);
+#if PYVR_B8_PF_DIST > 0
+                        if (i + PYVR_B8_PF_DIST < run_end) {
+                            // A/B builds only (measured: no help, abi.cu choose_layout): ask L2 now for the bricks of a later
+                            // sample of this run.  Four taps of alternating parity reach every brick the sample touches
+                            // unless it straddles brick faces on all three axes (1 in 8).
+                            const float fp = fi + (float)PYVR_B8_PF_DIST;
+                            const int QX = __float2int_rd(fmaf(fp, DX, X0)) - ogx + 1, QY = __float2int_rd(fmaf(fp, DY, Y0)) - ogy + 1,
+                                      QZ = __float2int_rd(fmaf(fp, DZ, Z0)) - ogz + 1;
+                            const IDX qx0 = (IDX)(QX >> 1) * PX8, qx1 = (IDX)((QX + 1) >> 1) * PX8;
+                            const IDX qy0 = (IDX)(QY >> 1) * PY8, qy1 = (IDX)((QY + 1) >> 1) * PY8;
+                            const IDX qz0 = (IDX)((QZ >> 1) << 3), qz1 = (IDX)(((QZ + 1) >> 1) << 3);
+                            prefetch_line(a.tap_base + (long long)(qx0 + qy0 + qz0) * TEXEL_BYTES);
+                            prefetch_line(a.tap_base + (long long)(qx1 + qy1 + qz0) * TEXEL_BYTES);
+                            prefetch_line(a.tap_base + (long long)(qx1 + qy0 + qz1) * TEXEL_BYTES);
+                            prefetch_line(a.tap_base + (long long)(qx0 + qy1 + qz1) * TEXEL_BYTES);
+                        }
+#endif
+                    } else {
                     const IDX e = (IDX)(ix - ogx) * (IDX)vol.pitch_x + (IDX)(iy - ogy) * (IDX)vol.pitch_y + (IDX)(iz - ogz);
                     const char *p00 = a.tap_base + (long long)e * ENTRY_BYTES;
                     const char *p01 = p00 + a.stride_y, *p10 = p00 + a.stride_x, *p11 = p10 + a.stride_y;
@@ -667,7 +721,6 @@ march_kernel(const __grid_constant__ MarchArgs a) {
                     // eight 4-byte gathers cost the L1 data stage about as much as the four 32-byte ones they
                     // replace (the stage is paid per quarter-warp pass, not per byte), so even the dense march,
                     // where 79 % of the samples are transparent, got 6 % slower.
-                    bool fetch = true;
 #if PYVR_DENSITY_FIRST
                     if (warp_transparent) {
                         constexpr int ZOFF = HALF ? 8 : 16;    // texel(iz + 1): the next entry, or the second half of a z-pair
@@ -679,7 +732,6 @@ march_kernel(const __grid_constant__ MarchArgs a) {
                     }
 #endif
                     if (fetch) {
-                    Texel2 c000, c001, c010, c011, c100, c101, c110, c111;
                     load_row<HALF, PAIR>(p00, c000, c001);
                     load_row<HALF, PAIR>(p01, c010, c011);
                     load_row<HALF, PAIR>(p10, c100, c101);
@@ -703,6 +755,9 @@ march_kernel(const __grid_constant__ MarchArgs a) {
                         prefetch_line(q + a.stride_x + a.stride_y);
                     }
 #endif
+                    }   // fetch
+                    }   // row layouts
+                    if (fetch) {
                     // filter order of the oracle: z (memory-fastest) first, then y, then x; {s, nx} and {ny, nz} packed
                     const f32x2 tz2 = pack2(wz, wz), ty2 = pack2(wy, wy), tx2 = pack2(wx, wx);
                     float density, nx, ny, nz;
@@ -753,10 +808,10 @@ march_kernel(const __grid_constant__ MarchArgs a) {
     }   // one tile (PYVR_PERSISTENT: next ticket)
 }
 
-template <bool STRICT, bool HALF, typename IDX, bool BRICK, bool PAIR, bool TEX = false>
+template <bool STRICT, bool HALF, typename IDX, bool BRICK, int LAYOUT, bool TEX = false>
 cudaError_t launch_one(const MarchArgs &a, int n_views, cudaStream_t stream) {
     const size_t smem = lut_smem_bytes(a.lut_size);
-    auto kern = march_kernel<STRICT, HALF, IDX, BRICK, PAIR, TEX>;
+    auto kern = march_kernel<STRICT, HALF, IDX, BRICK, LAYOUT, TEX>;
     // dynamic + static shared memory above the 48 KiB default needs the opt-in (static = the interval table)
     static size_t static_smem = ~(size_t)0;
     if (static_smem == ~(size_t)0) {
@@ -796,34 +851,36 @@ cudaError_t launch_one(const MarchArgs &a, int n_views, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
-template <bool HALF, bool PAIR>
+template <bool HALF, int LAYOUT>
 cudaError_t launch_fast(const MarchArgs &a, int n_views, bool wide, cudaStream_t stream) {
     if (a.vol.bricked)
-        return wide ? launch_one<false, HALF, long long, true, PAIR>(a, n_views, stream)
-                    : launch_one<false, HALF, int, true, PAIR>(a, n_views, stream);
-    return wide ? launch_one<false, HALF, long long, false, PAIR>(a, n_views, stream)
-                : launch_one<false, HALF, int, false, PAIR>(a, n_views, stream);
+        return wide ? launch_one<false, HALF, long long, true, LAYOUT>(a, n_views, stream)
+                    : launch_one<false, HALF, int, true, LAYOUT>(a, n_views, stream);
+    return wide ? launch_one<false, HALF, long long, false, LAYOUT>(a, n_views, stream)
+                : launch_one<false, HALF, int, false, LAYOUT>(a, n_views, stream);
 }
 
 }  // namespace
 
 cudaError_t launch_march(const MarchArgs &a, int n_views, bool half_texels, bool wide_index, cudaStream_t stream) {
-    const bool pair = a.vol.pair != 0;
+    const int layout = a.vol.brick8 ? 2 : a.vol.pair ? 1 : 0;
     // bricks are marched by the fast path only (the STRICT twin of the oracle has no notion of ownership);
-    // STRICT is a test mode and always uses 64-bit indices
-    if ((a.flags & PYVR_FLAG_STRICT) != 0 && !a.vol.bricked) {
-        if (half_texels) return pair ? launch_one<true, true, long long, false, true>(a, n_views, stream)
-                                     : launch_one<true, true, long long, false, false>(a, n_views, stream);
-        return pair ? launch_one<true, false, long long, false, true>(a, n_views, stream)
-                    : launch_one<true, false, long long, false, false>(a, n_views, stream);
-    }
+    // STRICT is a test mode, always uses 64-bit indices and finds its texels through texel_index() whatever the layout
+    if ((a.flags & PYVR_FLAG_STRICT) != 0 && !a.vol.bricked)
+        return half_texels ? launch_one<true, true, long long, false, 0>(a, n_views, stream)
+                           : launch_one<true, false, long long, false, 0>(a, n_views, stream);
     if ((a.flags & PYVR_FLAG_HWTEX) != 0 && a.tex != 0)   // the texture object hides texel format and layout
-        return a.vol.bricked ? launch_one<false, false, int, true, false, true>(a, n_views, stream)
-                             : launch_one<false, false, int, false, false, true>(a, n_views, stream);
-    if (half_texels) return pair ? launch_fast<true, true>(a, n_views, wide_index, stream)
-                                 : launch_fast<true, false>(a, n_views, wide_index, stream);
-    return pair ? launch_fast<false, true>(a, n_views, wide_index, stream)
-                : launch_fast<false, false>(a, n_views, wide_index, stream);
+        return a.vol.bricked ? launch_one<false, false, int, true, 0, true>(a, n_views, stream)
+                             : launch_one<false, false, int, false, 0, true>(a, n_views, stream);
+    // 2x2x2 bricks multiply pitches by 8 before the index type is chosen: keep 32-bit indices to a quarter of the range
+    if (layout == 2) {
+        const bool wide = wide_index || (long long)((a.vol.n[0] + 3) >> 1) * a.vol.pitch_x * 8 >= (1LL << 30);
+        return half_texels ? launch_fast<true, 2>(a, n_views, wide, stream) : launch_fast<false, 2>(a, n_views, wide, stream);
+    }
+    if (half_texels) return layout == 1 ? launch_fast<true, 1>(a, n_views, wide_index, stream)
+                                        : launch_fast<true, 0>(a, n_views, wide_index, stream);
+    return layout == 1 ? launch_fast<false, 1>(a, n_views, wide_index, stream)
+                       : launch_fast<false, 0>(a, n_views, wide_index, stream);
 }
 
 }  // namespace pyvr

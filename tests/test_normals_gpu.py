@@ -46,6 +46,41 @@ def test_ragged_and_vector_paths_vs_oracle(shape):
     _check(compute_normal_volume(vol), oracle.normals(vol), str(shape))
 
 
+@pytest.mark.parametrize("scale", [1e-45, 1e-38, 1e-30, 1e-26, 1e-20, 1e-16, 1e-12, 1e-8, 1.0, 1e6, 1e10, 1e19, 1e30])
+def test_extreme_magnitudes_stay_bit_exact(scale):
+    """The TMA kernel computes sqrt and the three quotients with nvcc's own fast-path sequences, branch-free, and
+    falls back to sqrtf() and "/" outside the range on which they are exact (normals.cu, finish_fast).  Sweep the
+    gradient magnitude across that range's edges -- denormals, 2^-100, 2^-75, huge values -- with mixed magnitudes
+    inside one voxel, exact zeros, negative zeros and flat runs."""
+    rng = np.random.default_rng(int(-np.log10(scale) + 50))
+    shape = (12, 16, 64)
+    base = rng.standard_normal(shape).astype(np.float32)
+    mix = np.float32(10.0) ** rng.integers(-12, 1, shape).astype(np.float32)       # up to 12 decades inside a stencil
+    data = (base * mix * np.float32(scale)).astype(np.float32)
+    data[2:5, 3:9, 8:40] = np.float32(0.0)                                         # flat: zero gradients
+    data[6:8, :, 16:24] = np.float32(-0.0)
+    data[9, 4:12, :] = data[9, 4, 0]                                               # flat along one axis only
+    with np.errstate(all="ignore"):
+        want = oracle.normals(data)
+        got = compute_normal_volume(data)
+    finite = np.isfinite(want)
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    assert np.array_equal(got.view(np.uint32)[finite], want.view(np.uint32)[finite]), f"scale {scale}: not bit-exact"
+
+
+def test_non_finite_voxels_propagate_like_numpy():
+    data = np.random.default_rng(3).random((8, 8, 32)).astype(np.float32)
+    data[3, 3, 7] = np.inf
+    data[5, 2, 20] = np.nan
+    data[1, 6, 12] = np.float32(3e38)
+    with np.errstate(all="ignore"):
+        want = oracle.normals(data)
+        got = compute_normal_volume(data)
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    ok = ~np.isnan(want)
+    assert np.array_equal(got.view(np.uint32)[ok], want.view(np.uint32)[ok])
+
+
 def test_large_volume_vs_oracle_and_timing():
     vol = create_sample_volume(256, "helix")
     got, ms = _cabi.compute_normals_host(vol, return_ms=True)

@@ -168,7 +168,7 @@ def test_non_cubic_volume():
         assert_parity(got, want)
 
 
-@pytest.mark.parametrize("size", [1, 2, 17, 256, 1024])
+@pytest.mark.parametrize("size", [1, 2, 17, 256, 1024, 3000, 4096])   # 3000: static + dynamic shared memory just above 48 KiB
 def test_lut_sizes(size):
     data = create_sample_volume(32, "sphere")
     vol = Volume(data=data, normals=oracle.normals(data))
@@ -208,6 +208,32 @@ def test_layouts_are_bit_identical(c1, layout):
         finally:
             del os.environ["PYVR_CUDA_LAYOUT"]
     assert np.array_equal(out["linear"].view(np.uint32), out[layout].view(np.uint32))
+
+
+@pytest.mark.parametrize("texel_format", ["f32", "f16"])
+@pytest.mark.parametrize("shape", [(64, 64, 64), (33, 47, 58)])
+def test_brick8_layout_is_bit_identical(texel_format, shape):
+    """2x2x2-texel bricks (the layout for sparse rays, option "brick8") hold the same texels as the row layouts:
+    fast and STRICT marches give the same float image, odd sizes and the apron included."""
+    rng = np.random.default_rng(5)
+    data = rng.random(shape, dtype=np.float32)
+    normals = rng.standard_normal(shape + (3,)).astype(np.float32)
+    vol = Volume(data=data, normals=normals)
+    lut = build_rgba_lut(ColorTransferFunction.from_colormap("viridis"), OpacityTransferFunction.linear(0.0, 0.2))
+    for strict in (False, True):
+        out = {}
+        for b8 in ("0", "1"):
+            os.environ["PYVR_CUDA_BRICK8"] = b8
+            try:
+                with VolumeRenderer(160, 96, config=RenderConfig.balanced(), light=Light.directional([1, -1, 0]),
+                                    texel_format=texel_format, strict=strict) as r:
+                    r.load_volume(vol)
+                    r.set_camera(turntable_camera(77))
+                    r.set_lut(lut)
+                    out[b8] = r.render_accum()
+            finally:
+                del os.environ["PYVR_CUDA_BRICK8"]
+        assert np.array_equal(out["0"].view(np.uint32), out["1"].view(np.uint32)), (texel_format, shape, strict)
 
 
 def test_render_without_volume_or_camera_returns_cleared_frame():
