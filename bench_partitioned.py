@@ -253,8 +253,7 @@ def parity_check(rank, world, local_rank):
     """The multi-process paths against the single-GPU frame, on C1's volume (128^3 double_sphere + normals, balanced,
     isometric view) at 400x300: (1) image tiles: reduce(SUM) of the per-rank frames == the single-GPU frame, bit for
     bit; (2) sort-last bricks + binary swap (p2p and nccl exchange): within max |delta| <= 3/255, >= 99.9 % of the
-    pixels within 1/255 (the merge clips saturating rays to alpha 0.99); brick sample counts
-    add up to the single-GPU count; (3) relay: bit-identical; (4) on rank 0 the single-GPU frame itself against the
+    pixels within 1/255 (the merge clips saturating rays to alpha 0.99); (3) relay: bit-identical; (4) on rank 0 the single-GPU frame itself against the
     CPU oracle within BASELINE.json's tolerance.  Returns a dict on rank 0, None elsewhere."""
     import torch
     import torch.distributed as dist
@@ -327,7 +326,9 @@ def parity_check(rank, world, local_rank):
                 if rank == 0:
                     m = metrics(frame_of(frame), want)
                     m["ok"] = bool(m["max_abs"] <= 3 and m["frac_within_1"] >= 0.999)
-                    m["brick_samples_add_up"] = bool(int(samples.item()) == want_samples)
+                    # every sample lands in exactly one brick, but a back brick cannot see that the shader stopped the
+                    # ray in front of it (alpha >= 0.99), so the bricks execute a few more samples than the single pass
+                    m["brick_samples_over_single_gpu"] = int(samples.item()) / max(want_samples, 1)
                     out[f"sort_last_{exchange}"] = m
                 session.close()
             relay = mg.RelaySession(data.shape, vol.min_bounds, vol.max_bounds, W * H, device=local_rank)

@@ -101,7 +101,8 @@ typedef struct {
 /* --- life cycle: ModernGLManager.__init__ / cleanup (manager.py:14-41, 238-256) ------------------ */
 int pyvr_cuda_create(int device, int width, int height, pyvr_ctx **out_ctx);
 int pyvr_cuda_destroy(pyvr_ctx *ctx);
-/* Run all work of this context on an existing cudaStream_t (0 = the context's own stream). */
+/* Run all work of this context on an existing cudaStream_t.  0 = the context's own non-blocking stream; the legacy
+ * default stream has to be named by its explicit handle cudaStreamLegacy ((cudaStream_t)0x1). */
 int pyvr_cuda_set_stream(pyvr_ctx *ctx, void *cuda_stream);
 
 /* --- create_volume_texture + create_normal_texture + bounds uniforms
@@ -213,10 +214,12 @@ int pyvr_cuda_composite_finalize(int device, const float *front, const float *ba
  * comparison is wrap-safe).  They replace host barriers / NCCL fences around peer reads and writes. */
 int pyvr_cuda_flag_signal(int device, uint32_t *flag, uint32_t value, void *cuda_stream);
 int pyvr_cuda_flag_wait(int device, const uint32_t *flags, int n_flags, uint32_t value, void *cuda_stream);
-/* Plain cudaMalloc memory (IPC-exportable, unlike a sub-allocation of a framework's caching pool). */
+/* Plain cudaMalloc memory, rounded up to whole 2 MiB blocks so that the buffer is an allocation of its own: a CUDA
+ * IPC handle names the enclosing allocation, and the driver packs smaller requests into shared blocks. */
 int pyvr_cuda_device_alloc(int device, size_t bytes, void **out);
 int pyvr_cuda_device_free(int device, void *ptr);
-/* CUDA IPC: share a pyvr_cuda_device_alloc buffer with the other single-GPU processes of the node. */
+/* CUDA IPC: share a pyvr_cuda_device_alloc buffer with the other single-GPU processes of the node.  export fails
+ * with PYVR_ERR_INVALID if ptr is not the start of an allocation. */
 int pyvr_cuda_ipc_export(int device, void *ptr, uint8_t handle[PYVR_IPC_HANDLE_BYTES]);
 int pyvr_cuda_ipc_open(int device, const uint8_t handle[PYVR_IPC_HANDLE_BYTES], void **out);
 int pyvr_cuda_ipc_close(int device, void *ptr);

@@ -1038,10 +1038,17 @@ int pyvr_cuda_flag_wait(int device, const uint32_t *flags, int n_flags, uint32_t
     return PYVR_OK;
 }
 
+// The driver packs cudaMalloc requests below 2 MiB into shared 2 MiB blocks, and a CUDA IPC handle names the BLOCK:
+// the process that opens it gets the block's base address, not the buffer's (round 2: a 1.9 MB partial image read by
+// its binary-swap partner at the wrong offset).  Every buffer handed out here is therefore a whole number of 2 MiB,
+// i.e. an allocation of its own, and pyvr_cuda_ipc_export refuses pointers that are not the start of one.
+constexpr size_t kIpcGranule = (size_t)2 << 20;
+
 int pyvr_cuda_device_alloc(int device, size_t bytes, void **out) {
     if (!out) return fail(PYVR_ERR_INVALID, "out is NULL");
     DeviceGuard guard(device);
-    CU(cudaMalloc(out, bytes));
+    const size_t rounded = ((bytes > 0 ? bytes : 1) + kIpcGranule - 1) / kIpcGranule * kIpcGranule;
+    CU(cudaMalloc(out, rounded));
     return PYVR_OK;
 }
 
@@ -1055,6 +1062,19 @@ int pyvr_cuda_ipc_export(int device, void *ptr, uint8_t handle[PYVR_IPC_HANDLE_B
     if (!ptr || !handle) return fail(PYVR_ERR_INVALID, "NULL argument");
     static_assert(sizeof(cudaIpcMemHandle_t) == PYVR_IPC_HANDLE_BYTES, "IPC handle size");
     DeviceGuard guard(device);
+    {   // the handle would map the enclosing allocation: insist that `ptr` starts one (cuMemGetAddressRange)
+        typedef int (*RangeFn)(unsigned long long *, size_t *, unsigned long long);
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess && fn) {
+            unsigned long long base = 0;
+            size_t size = 0;
+            if (reinterpret_cast<RangeFn>(fn)(&base, &size, (unsigned long long)(uintptr_t)ptr) == 0 &&
+                base != (unsigned long long)(uintptr_t)ptr)
+                return fail(PYVR_ERR_INVALID, "IPC export needs the start of an allocation (use pyvr_cuda_device_alloc)");
+        }
+    }
     cudaIpcMemHandle_t h;
     CU(cudaIpcGetMemHandle(&h, ptr));
     memcpy(handle, &h, sizeof h);

@@ -352,7 +352,8 @@ class CudaVolumeRenderer:
         return out
 
     def set_stream(self, cuda_stream: int) -> None:
-        """Run this renderer's work on an existing ``cudaStream_t`` (e.g. torch's current stream)."""
+        """Run this renderer's work on an existing ``cudaStream_t`` (e.g. torch's current stream).  ``0`` selects the
+        renderer's own non-blocking stream; pass ``1`` (``cudaStreamLegacy``) for the legacy default stream."""
         _cabi.check(self._lib.pyvr_cuda_set_stream(self._ctx, ctypes.c_void_p(cuda_stream)))
 
     @property

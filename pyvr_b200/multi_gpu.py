@@ -452,6 +452,7 @@ class SortLastSession:
         self._k = len(self.plan)
         self._flags = PeerFlags(self.dist, self.group, self.device, slots=2 * self._k + 2)
         self._frame_no = 0
+        self._released = 0
         self._finalized_to = None
 
     def _dst_frame_ptr(self, dst: int) -> int:
@@ -556,14 +557,29 @@ class SortLastSession:
     def begin_frame(self):
         """p2p exchange: call before the march of the next frame (in stream order).  The partial image may be
         overwritten only after every partner has finished reading it, and a piece may be written into rank dst's frame
-        only after dst has consumed the previous frame."""
+        only after dst has let go of the previous frame -- which it does here at the latest (see :meth:`release`)."""
         if self.exchange != "p2p" or self._frame_no == 0:
             return
         stream = self.torch.cuda.current_stream().cuda_stream
         for r, step in enumerate(self.plan):
             self._flags.wait(self._k + r, step.partner, self._frame_no, stream)
-        if self._gather_dst is not None and self.rank != self._gather_dst:
-            self._flags.wait(2 * self._k + 1, self._gather_dst, self._frame_no, stream)
+        if self._gather_dst is not None:
+            if self.rank == self._gather_dst:
+                self.release()
+            else:
+                self._flags.wait(2 * self._k + 1, self._gather_dst, self._frame_no, stream)
+
+    def release(self):
+        """p2p exchange, rank ``dst``: the frame returned by :meth:`gather_rgba8` has been consumed (in the order of
+        the current stream); the other ranks may store the next frame's pieces into it.  Called implicitly when the
+        next frame begins, so a frame stays valid until then."""
+        if self.exchange != "p2p" or self._gather_dst != self.rank or self._released == self._frame_no:
+            return
+        stream = self.torch.cuda.current_stream().cuda_stream
+        for r in range(self.world):
+            if r != self.rank:
+                self._flags.signal(r, 2 * self._k + 1, self._frame_no, stream)
+        self._released = self._frame_no
 
     # -- final frame -----------------------------------------------------------------------------
     def gather_rgba8(self, piece_range, piece, flags: int = 0, dst: int = 0):
@@ -585,10 +601,7 @@ class SortLastSession:
             self._gather_dst = dst
             self._flags.signal(dst, 2 * k, self._frame_no, stream)
             if self.rank == dst:
-                self._flags.wait_all(2 * k, self._frame_no, stream)
-                for r in range(self.world):      # the frame is complete; peers may write the next one once dst moves on
-                    if r != dst:
-                        self._flags.signal(r, 2 * k + 1, self._frame_no, stream)
+                self._flags.wait_all(2 * k, self._frame_no, stream)      # the frame is complete; release() lets go of it
             if self._bound is None:       # the next march may run on another stream: it must not overwrite the image
                 torch.cuda.current_stream().synchronize()   # while a peer's merge or this finalize still reads it
                 self.dist.barrier(group=self.group)
@@ -629,6 +642,9 @@ class SortLastSession:
         self._own = self._frame = None
 
 
+CUDA_STREAM_LEGACY = 0x1     # cudaStreamLegacy: the explicit handle of the legacy default stream
+
+
 def _bind_stream(session, renderer):
     """Stream discipline of the executors: merges, finalize, NCCL traffic and fences are enqueued on torch's
     CURRENT stream, so the renderer must march on that stream too -- otherwise the next frame's march could
@@ -637,7 +653,10 @@ def _bind_stream(session, renderer):
     that was never bound falls back to host synchronisation around every frame."""
     stream = session.torch.cuda.current_stream().cuda_stream
     if session._bound != (id(renderer), stream):
-        renderer.set_stream(stream)
+        # torch's default stream has handle 0, which pyvr_cuda_set_stream reads as "the context's own (non-blocking)
+        # stream"; name the legacy default stream by its explicit handle instead (cudaStreamLegacy = 0x1).  Found by
+        # the 2-GPU parity check of round 2: merges on stream 0 raced the march on the renderer's own stream.
+        renderer.set_stream(stream if stream else CUDA_STREAM_LEGACY)
         session._bound = (id(renderer), stream)
 
 
