@@ -188,10 +188,14 @@ int pyvr_cuda_render_accum_relay(pyvr_ctx *ctx, const float *in_accum, float *ou
 int pyvr_cuda_get_stats(pyvr_ctx *ctx, pyvr_stats *out);
 
 /* --- compute_normal_volume (pyvr/datasets/synthetic.py:109-122) ----------------------------------
- * in: n0*n1*n2 floats (C order); out: n0*n1*n2*3 floats.  buffers_are_device != 0: both are device
- * pointers on `device`.  kernel_ms (may be NULL) receives the stencil kernel's device time. */
+ * in: n0*n1*n2 floats (C order); out: n0*n1*n2*3 floats.  flags: PYVR_NORMALS_DEVICE_BUFFERS = both are device
+ * pointers on `device`; PYVR_NORMALS_RELAXED = quotients as g * (1/norm), within 2 ulp of the reference's divisions
+ * (the path's tolerance is 1e-5 relative) instead of bit-identical to them.  kernel_ms (may be NULL) receives the
+ * stencil kernel's device time. */
+#define PYVR_NORMALS_DEVICE_BUFFERS 1
+#define PYVR_NORMALS_RELAXED 2
 int pyvr_cuda_compute_normals(int device, const float *in, float *out, int n0, int n1, int n2,
-                              int buffers_are_device, float *kernel_ms);
+                              int flags, float *kernel_ms);
 
 /* --- sort-last compositing (no reference counterpart) ----------------------------------------------
  * Partial images are the pre-blend fragment colours pyvr_cuda_render_accum produces: n_pixels * 4 floats
@@ -234,7 +238,9 @@ int pyvr_cuda_stream_synchronize(int device, void *cuda_stream);
 int pyvr_cuda_set_option(pyvr_ctx *ctx, const char *key, int value);
 /* Roofline denominators measured on the spot (no reference counterpart; csrc/bandwidth.cu): bytes per second
  * delivered to registers by coalesced 128-bit loads that hit L1 (level 1: the SM load-return path that bounds
- * the march's texel gather) or stream from L2 with L1 bypassed (level 2).  *gbs in 1e9 bytes/s. */
+ * the march's texel gather) or stream from L2 with L1 bypassed (level 2); level 3: the DRAM rate of a streaming
+ * kernel with the normals stencil's traffic mix (4 bytes read, 12 written per element, no arithmetic), which a
+ * 1:1 copy rate overstates.  *gbs in 1e9 bytes/s. */
 int pyvr_cuda_measure_cache_bandwidth(int device, int level, double *gbs);
 /* Page-locked host memory for frame read-back at full PCIe rate (cudaMallocHost / cudaFreeHost). */
 int pyvr_cuda_host_alloc(size_t bytes, void **out);

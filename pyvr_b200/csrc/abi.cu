@@ -74,6 +74,7 @@ struct pyvr_ctx {
     bool shard_in_place = false;           // true: foreign pixels are left untouched (all ranks write one shared frame)
     int pair_option = -1;   // z-pair entries: -1 auto (when the doubled array stays under kPairBudget), 0 off, 1 on
     bool use_pair = false;  // decided per upload
+    const pyvr_view *launch_view = nullptr;   // host copy of the first view of the launch being prepared (row order)
     int brick8_option = 0;  // 2x2x2-texel bricks (common.cuh): 0 off (default: slower, see choose_layout), 1 on
     bool use_brick8 = false;
     cudaArray_t tex_array = nullptr;        // PYVR_FLAG_HWTEX: built on first use from the packed texels
@@ -357,6 +358,27 @@ MarchArgs make_args(const pyvr_ctx *c) {
     return a;
 }
 
+// Tile row in which the volume's centre appears (MarchArgs.first_row): CTAs are dispatched in block-index order, and
+// the march maps consecutive blockIdx.y to rows from that one outwards, so the tiles with the longest rays start
+// first and the empty rows at the top and bottom of the image finish the launch.  -1 = keep the natural order.
+int centre_row(const pyvr_ctx *c, const pyvr_view *vw) {
+    if (!vw) return -1;
+    double cdir[3], vv = 0.0, ww = 0.0, cv = 0.0, cw = 0.0;
+    for (int a = 0; a < 3; ++a) {
+        cdir[a] = 0.5 * ((double)c->vol.bmin[a] + (double)c->vol.bmax[a]) - (double)vw->origin[a];
+        vv += (double)vw->v[a] * vw->v[a]; ww += (double)vw->w[a] * vw->w[a];
+        cv += cdir[a] * vw->v[a]; cw += cdir[a] * vw->w[a];
+    }
+    if (!(vv > 0.0) || !(ww > 0.0) || !(cw > 0.0)) return -1;      // no closed-form basis, or the centre is behind the camera
+    const double ndy = (cv / vv) / (cw / ww);                       // dir = w + ndx*u + ndy*v, u, v, w orthogonal
+    const double py = (ndy * 0.5 + 0.5) * (double)c->height;
+    const int rows = (c->height + 7) / 8;                           // TILE_H = 8 (march.cu)
+    int row = (int)floor(py / 8.0);
+    if (row < 0) row = 0;
+    if (row > rows - 1) row = rows - 1;
+    return row;
+}
+
 // Launch the march for `n` views already resident in c->d_views[first..], timed with events.
 int march(pyvr_ctx *c, int first, int n, uchar4 *out8, float4 *out_acc, size_t ev_pair,
           const float4 *in_acc = nullptr) {
@@ -370,6 +392,10 @@ int march(pyvr_ctx *c, int first, int n, uchar4 *out8, float4 *out_acc, size_t e
     a.out8 = out8;
     a.out_acc = out_acc;
     a.in_acc = in_acc;
+    // measured on C4 (profiles/r02_c4_shard_probe.txt): whole frame 8.16 -> 7.83 ms, but one rank of an 8-way deal
+    // 1.43 -> 1.58 ms (its few heavy tiles then all start at once), so sharded launches keep the natural order
+    a.first_row = c->shard_count > 1 ? -1 : centre_row(c, c->launch_view);
+    c->launch_view = nullptr;
     if (c->shard_count > 1) {
         if (in_acc) return fail(PYVR_ERR_STATE, "relay rendering cannot be combined with image-space sharding");
         if (!c->shard_in_place) {   // the launch covers this rank's tiles only: everything else reads as cleared
@@ -837,6 +863,7 @@ int pyvr_cuda_render_batch(pyvr_ctx *c, const pyvr_view *views, int n, uint8_t *
         if (rc != PYVR_OK) return rc;
         for (int first = 0; first < n; first += chunk) {
             const int m = n - first < chunk ? n - first : chunk;
+            c->launch_view = views + first;
             rc = march(c, first, m, reinterpret_cast<uchar4 *>(out) + (size_t)first * frame_pixels(c), nullptr, pairs++);
             if (rc != PYVR_OK) return rc;
         }
@@ -854,6 +881,7 @@ int pyvr_cuda_render_batch(pyvr_ctx *c, const pyvr_view *views, int n, uint8_t *
             const int slot = g % kRing;
             if (g >= kRing) CU(cudaStreamWaitEvent(c->stream, c->slot_copied[slot], 0));
             uchar4 *frames = c->frames + (size_t)slot * kSlotViews * frame_pixels(c);
+            c->launch_view = views + first;
             rc = march(c, first, m, frames, nullptr, pairs++);
             if (rc != PYVR_OK) return rc;
             CU(cudaEventRecord(c->slot_rendered[slot], c->stream));
@@ -908,6 +936,7 @@ int pyvr_cuda_render_accum(pyvr_ctx *c, float *out, int out_is_device) {
     if (rc != PYVR_OK) return rc;
     CU(cudaMemcpyAsync(c->d_views, &c->view, sizeof(pyvr_view), cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemsetAsync(c->d_counters, 0, sizeof(unsigned long long) * CNT_N, c->stream));
+    c->launch_view = &c->view;
     rc = march(c, 0, 1, nullptr, target, 0);
     if (rc != PYVR_OK) return rc;
     if (!out_is_device) CU(cudaMemcpyAsync(out, c->accum, bytes, cudaMemcpyDeviceToHost, c->stream));
@@ -925,6 +954,7 @@ int pyvr_cuda_render_accum_relay(pyvr_ctx *c, const float *in_accum, float *out_
     if (rc != PYVR_OK) return rc;
     CU(cudaMemcpyAsync(c->d_views, &c->view, sizeof(pyvr_view), cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemsetAsync(c->d_counters, 0, sizeof(unsigned long long) * CNT_N, c->stream));
+    c->launch_view = &c->view;
     rc = march(c, 0, 1, nullptr, reinterpret_cast<float4 *>(out_accum), 0, reinterpret_cast<const float4 *>(in_accum));
     if (rc != PYVR_OK) return rc;
     return finish_stats(c, 1, 1);
@@ -937,7 +967,8 @@ int pyvr_cuda_get_stats(pyvr_ctx *c, pyvr_stats *out) {
 }
 
 int pyvr_cuda_compute_normals(int device, const float *in, float *out, int n0, int n1, int n2,
-                              int buffers_are_device, float *kernel_ms) {
+                              int flags, float *kernel_ms) {
+    const bool buffers_are_device = (flags & PYVR_NORMALS_DEVICE_BUFFERS) != 0, relaxed = (flags & PYVR_NORMALS_RELAXED) != 0;
     if (!in || !out) return fail(PYVR_ERR_INVALID, "NULL argument");
     if (n0 <= 0 || n1 <= 0 || n2 <= 0) return fail(PYVR_ERR_INVALID, "Volume data must be 3D with positive extents");
     int n_dev = 0;
@@ -959,7 +990,7 @@ int pyvr_cuda_compute_normals(int device, const float *in, float *out, int n0, i
     if (e == cudaSuccess) e = cudaEventCreate(&e0);
     if (e == cudaSuccess) e = cudaEventCreate(&e1);
     if (e == cudaSuccess) e = cudaEventRecord(e0, 0);
-    if (e == cudaSuccess) e = launch_normals(d_in, d_out, n0, n1, n2, 0);
+    if (e == cudaSuccess) e = launch_normals(d_in, d_out, n0, n1, n2, relaxed, 0);
     if (e == cudaSuccess) e = cudaEventRecord(e1, 0);
     if (e == cudaSuccess) e = cudaEventSynchronize(e1);
     if (e == cudaSuccess && kernel_ms) e = cudaEventElapsedTime(kernel_ms, e0, e1);
@@ -975,7 +1006,7 @@ int pyvr_cuda_compute_normals(int device, const float *in, float *out, int n0, i
 
 int pyvr_cuda_measure_cache_bandwidth(int device, int level, double *gbs) {
     if (!gbs) return fail(PYVR_ERR_INVALID, "gbs is NULL");
-    if (level != 1 && level != 2) return fail(PYVR_ERR_INVALID, "level must be 1 (L1) or 2 (L2)");
+    if (level < 1 || level > 3) return fail(PYVR_ERR_INVALID, "level must be 1 (L1), 2 (L2) or 3 (DRAM, 1:3 read:write mix)");
     int n_dev = 0;
     CU(cudaGetDeviceCount(&n_dev));
     if (device < 0 || device >= n_dev) return fail(PYVR_ERR_INVALID, "device %d out of range (%d visible)", device, n_dev);

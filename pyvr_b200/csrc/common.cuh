@@ -107,6 +107,7 @@ struct MarchArgs {
     // asked for in-place sharding into a frame that all ranks write).  shard_count <= 1: everything.
     int shard_rank, shard_count, shard_shift;
     int n_views;                   // views of this launch (filled by the launcher)
+    int first_row;                 // tile row dispatched first (the rows follow from it outwards); -1 = natural order
     unsigned *tile_counter;        // PYVR_PERSISTENT builds: ticket counter of the tile queue (zeroed per launch)
 };
 
@@ -167,7 +168,8 @@ cudaError_t launch_synth_volume(const VolumeDesc &vol, bool half_texels, int sha
 cudaError_t launch_linearize_texels(const VolumeDesc &vol, bool half_texels, int x0, int nx, void *dst, cudaStream_t stream);
 cudaError_t launch_unpack_texels(const VolumeDesc &vol, bool half_texels, float *scalar, float *normals,
                                  cudaStream_t stream);
-cudaError_t launch_normals(const float *in, float *out, int n0, int n1, int n2, cudaStream_t stream);
+// relaxed: quotients as g * (1/norm) (within 2 ulp; TMA kernel only) instead of correctly rounded divisions
+cudaError_t launch_normals(const float *in, float *out, int n0, int n1, int n2, bool relaxed, cudaStream_t stream);
 // bandwidth.cu: measured cache bandwidths (roofline denominators); level 1 = L1 load-return, 2 = L2 -> SM
 cudaError_t measure_cache_bandwidth(int level, double *gbs);
 

@@ -387,14 +387,23 @@ march_kernel(const __grid_constant__ MarchArgs a) {
     // image-space sharding (multi-GPU tiles): groups of 2^shift x 2^shift CTA tiles are dealt over the ranks along
     // image rows, every row of groups shifted by one rank against the one below: owner(gx, gy) = (gx + gy) mod P.
     // Only the owned tiles are launched: blockIdx.x enumerates this rank's groups of the row.
+    // Row order: CTAs start in block-index order.  Consecutive blockIdx.y are mapped to tile rows from first_row (where
+    // the volume's centre projects, abi.cu) outwards, alternating below / above, so the rows with the longest rays
+    // start first and the launch ends on rows that miss the volume (a single 16x8 tile through the middle of C4 runs
+    // for about a millisecond): 8.16 -> 7.83 ms per C4 frame on one GPU, nothing on C3 (profiles/r02_c4_shard_probe.txt).
+    int block_y = blockIdx.y;
+    if (a.first_row >= 0) {
+        const int rows = gridDim.y, cy = a.first_row, m = min(cy, rows - 1 - cy), k = blockIdx.y;
+        block_y = k <= 2 * m ? cy + ((k & 1) ? (k + 1) / 2 : -(k / 2)) : (cy <= rows - 1 - cy ? k : rows - 1 - k);
+    }
     int tile_x = blockIdx.x;
     if (a.shard_count > 1) {
-        const int sh = a.shard_shift, gy = blockIdx.y >> sh, k = blockIdx.x >> sh;
+        const int sh = a.shard_shift, gy = block_y >> sh, k = blockIdx.x >> sh;
         const int first = (a.shard_rank - gy % a.shard_count + a.shard_count) % a.shard_count;
         tile_x = ((first + k * a.shard_count) << sh) + (blockIdx.x & ((1 << sh) - 1));
         if (tile_x * TILE_W >= a.width) return;
     }
-    const int tile_y = blockIdx.y, view_index = blockIdx.z, wsub = warp;
+    const int tile_y = block_y, view_index = blockIdx.z, wsub = warp;
     {
 #endif
     const int px = tile_x * TILE_W + (wsub % CTA_WX) * WARP_W + lane_x;

@@ -166,13 +166,17 @@ def view_from_camera(camera, aspect: float) -> View:
     return view_from_matrices(camera.get_view_matrix(), camera.get_projection_matrix(aspect), position)
 
 
-def compute_normals_host(volume: np.ndarray, device: int = 0, return_ms: bool = False):
+NORMALS_DEVICE_BUFFERS, NORMALS_RELAXED = 1, 2     # pyvr_cuda_compute_normals flags
+
+
+def compute_normals_host(volume: np.ndarray, device: int = 0, return_ms: bool = False, relaxed: bool = False):
     """Host array in, host array out, through ``pyvr_cuda_compute_normals``."""
     vol = np.ascontiguousarray(volume, dtype=np.float32)
     out = np.empty(vol.shape + (3,), dtype=np.float32)
     ms = _c.c_float(0.0)
     check(lib().pyvr_cuda_compute_normals(device, vol.ctypes.data, out.ctypes.data,
-                                          vol.shape[0], vol.shape[1], vol.shape[2], 0, _c.byref(ms)))
+                                          vol.shape[0], vol.shape[1], vol.shape[2],
+                                          NORMALS_RELAXED if relaxed else 0, _c.byref(ms)))
     return (out, ms.value) if return_ms else out
 
 

@@ -70,15 +70,17 @@ def create_sample_volume(size: int = 64, shape: str = "sphere") -> np.ndarray:
     return vol.astype(np.float32)
 
 
-def compute_normal_volume(volume: np.ndarray) -> np.ndarray:
+def compute_normal_volume(volume: np.ndarray, relaxed: bool = False) -> np.ndarray:
     """Normalised central-difference gradient, ``(D, H, W) -> (D, H, W, 3) float32``.
 
     Runs on ``cuda:0`` through ``pyvr_cuda_compute_normals`` (host buffers in,
-    host buffers out).  Component order follows the numpy axes (0, 1, 2).
+    host buffers out).  Component order follows the numpy axes (0, 1, 2).  The result is bit-identical
+    to the reference's numpy function; ``relaxed=True`` (not in the reference) trades that for speed:
+    quotients within 2 ulp (the path's tolerance is 1e-5 relative).
     """
     from .cuda_renderer import _cabi
 
     vol = np.ascontiguousarray(volume, dtype=np.float32)
     if vol.ndim != 3:
         raise ValueError(f"Volume data must be 3D, got shape {vol.shape}")
-    return _cabi.compute_normals_host(vol)
+    return _cabi.compute_normals_host(vol, relaxed=relaxed)

@@ -68,6 +68,16 @@ def test_extreme_magnitudes_stay_bit_exact(scale):
     assert np.array_equal(got.view(np.uint32)[finite], want.view(np.uint32)[finite]), f"scale {scale}: not bit-exact"
 
 
+def test_relaxed_opt_in_stays_within_the_tolerance():
+    """compute_normal_volume(relaxed=True): g * (1/norm) instead of three correctly rounded quotients."""
+    data = create_sample_volume(96, "double_sphere")
+    want = oracle.normals(data)
+    got = compute_normal_volume(data, relaxed=True)
+    assert np.all(np.abs(got - want) <= 1e-5 * np.maximum(1.0, np.abs(want)))
+    ulp = np.abs(got.view(np.int32).astype(np.int64) - want.view(np.int32).astype(np.int64))
+    assert ulp.max() <= 2 and np.array_equal(np.signbit(got), np.signbit(want))
+
+
 def test_non_finite_voxels_propagate_like_numpy():
     data = np.random.default_rng(3).random((8, 8, 32)).astype(np.float32)
     data[3, 3, 7] = np.inf
