@@ -139,27 +139,26 @@ def measure(args, rank, world, local_rank, workload, steps, warmup, size=None, w
         nonlocal frame, frame_ptr
         if read_back:
             renderer.set_camera(camera)                      # camera uniforms travel host -> device again
+        # the sessions make device-output renders asynchronous: the exchange is enqueued behind the march while it
+        # runs, and the counters are read (renderer.stats waits for them) only after everything has been enqueued
         if session is not None:
             renderer.render_accum_to_device(session.image_ptr())
-            st = renderer.stats
             piece_range, piece = session.composite(position, finalize_to=0 if args.exchange == "p2p" else None)
             out = session.gather_rgba8(piece_range, piece)
             if out is not None:
                 frame_ptr = out if isinstance(out, int) else out.data_ptr()
         elif tiles is not None:
             out = tiles.render()                 # march + peer stores into rank 0's frame + two flags
-            st = renderer.stats
             if out is not None:
                 frame_ptr = out
         else:
             renderer.render_to_device(frame.data_ptr())
-            st = renderer.stats
         if read_back and rank == 0:
             _cabi.check(_cabi.lib().pyvr_cuda_memcpy(local_rank, pinned.array.ctypes.data, ctypes.c_void_p(frame_ptr),
                                                      n_pixels * 4, 2, ctypes.c_void_p(stream.cuda_stream)))
         if tiles is not None:
             tiles.release()
-        return st
+        return renderer.stats
 
     for _ in range(args.warmup):
         step()

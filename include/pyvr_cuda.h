@@ -218,6 +218,24 @@ int pyvr_cuda_composite_finalize(int device, const float *front, const float *ba
  * comparison is wrap-safe).  They replace host barriers / NCCL fences around peer reads and writes. */
 int pyvr_cuda_flag_signal(int device, uint32_t *flag, uint32_t value, void *cuda_stream);
 int pyvr_cuda_flag_wait(int device, const uint32_t *flags, int n_flags, uint32_t value, void *cuda_stream);
+/* The same release store to n flags (one per peer) in one launch. */
+int pyvr_cuda_flag_signal_many(int device, uint32_t *const *flags, int n_flags, uint32_t value, void *cuda_stream);
+/* A whole binary swap in one call: per round [signal_before] -> wait(wait_flag >= value) -> merge -> signal(signal_done,
+ * signal_next), enqueued back to back on the stream (a Python loop over the single calls leaves the GPU idle between
+ * them: 8 GPUs, 3 rounds, ~0.3 ms per frame).  A round with out8 != NULL is the fused last round
+ * (pyvr_cuda_composite_finalize); otherwise pyvr_cuda_composite_over into `out`.  NULL flag pointers are skipped. */
+typedef struct {
+    const float *front, *back;   /* n_pixels float4 each; either may be peer-mapped */
+    float *out;                  /* merged floats (may alias front or back); may be NULL when out8 is set */
+    uint8_t *out8;               /* NULL, or the RGBA8 destination of the fused last round (may be peer-mapped) */
+    uint64_t n_pixels;
+    uint32_t *signal_before;     /* partner's counter: "my image of this round is complete" (round 0) */
+    const uint32_t *wait_flag;   /* own counter: the partner's image of this round is complete */
+    uint32_t *signal_done;       /* partner's counter: "I have finished reading your image" */
+    uint32_t *signal_next;       /* next partner's counter: "my image of the next round is complete" */
+} pyvr_swap_round;
+int pyvr_cuda_binary_swap(int device, const pyvr_swap_round *rounds, int n_rounds, uint32_t value,
+                          float termination_alpha, uint32_t flags, void *cuda_stream);
 /* Plain cudaMalloc memory, rounded up to whole 2 MiB blocks so that the buffer is an allocation of its own: a CUDA
  * IPC handle names the enclosing allocation, and the driver packs smaller requests into shared blocks. */
 int pyvr_cuda_device_alloc(int device, size_t bytes, void **out);

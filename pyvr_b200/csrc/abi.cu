@@ -74,6 +74,11 @@ struct pyvr_ctx {
     bool shard_in_place = false;           // true: foreign pixels are left untouched (all ranks write one shared frame)
     int pair_option = -1;   // z-pair entries: -1 auto (when the doubled array stays under kPairBudget), 0 off, 1 on
     bool use_pair = false;  // decided per upload
+    bool async_device = false;      // option "async_device_output": device-output renders return without a host sync
+    bool stats_pending = false;     // counters of the last render are on their way to h_counters (stats_ready)
+    size_t pending_pairs = 0;
+    int pending_views = 0;
+    cudaEvent_t stats_ready = nullptr;
     const pyvr_view *launch_view = nullptr;   // host copy of the first view of the launch being prepared (row order)
     int brick8_option = 0;  // 2x2x2-texel bricks (common.cuh): 0 off (default: slower, see choose_layout), 1 on
     bool use_brick8 = false;
@@ -409,12 +414,12 @@ int march(pyvr_ctx *c, int first, int n, uchar4 *out8, float4 *out_acc, size_t e
     return PYVR_OK;
 }
 
-int finish_stats(pyvr_ctx *c, size_t pairs, int views) {
-    CU(cudaMemcpyAsync(c->h_counters, c->d_counters, sizeof(unsigned long long) * CNT_N,
-                       cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
+int resolve_stats(pyvr_ctx *c) {
+    if (!c->stats_pending) return PYVR_OK;
+    c->stats_pending = false;
+    CU(cudaEventSynchronize(c->stats_ready));
     float total = 0.0f;
-    for (size_t i = 0; i < pairs; ++i) {
+    for (size_t i = 0; i < c->pending_pairs; ++i) {
         float ms = 0.0f;
         CU(cudaEventElapsedTime(&ms, c->ev[2 * i], c->ev[2 * i + 1]));
         total += ms;
@@ -424,9 +429,21 @@ int finish_stats(pyvr_ctx *c, size_t pairs, int views) {
     c->stats.rays_hit = c->h_counters[CNT_HIT];
     c->stats.rays_terminated = c->h_counters[CNT_TERM];
     c->stats.kernel_ms = total;
-    c->stats.kernel_launches = (uint32_t)pairs;
-    c->stats.views = (uint32_t)views;
+    c->stats.kernel_launches = (uint32_t)c->pending_pairs;
+    c->stats.views = (uint32_t)c->pending_views;
     return PYVR_OK;
+}
+
+// Counters -> pyvr_stats.  defer (device output with option "async_device_output"): the copy of the counters is
+// enqueued and the call returns; pyvr_cuda_get_stats waits for it.  Otherwise the stream is synchronised here.
+int finish_stats(pyvr_ctx *c, size_t pairs, int views, bool defer = false) {
+    CU(cudaMemcpyAsync(c->h_counters, c->d_counters, sizeof(unsigned long long) * CNT_N,
+                       cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaEventRecord(c->stats_ready, c->stream));
+    c->stats_pending = true;
+    c->pending_pairs = pairs;
+    c->pending_views = views;
+    return defer ? PYVR_OK : resolve_stats(c);
 }
 
 bool renderable(const pyvr_ctx *c) { return c->have_volume && c->lut_size > 0; }
@@ -475,6 +492,7 @@ int pyvr_cuda_create(int device, int width, int height, pyvr_ctx **out_ctx) {
     if (e == cudaSuccess) e = cudaMalloc(&c->frames, frame_pixels(c) * sizeof(uchar4) * kRing * kSlotViews);
     if (e == cudaSuccess) e = cudaMalloc(&c->d_counters, sizeof(unsigned long long) * (CNT_N + 1));   // + tile-queue ticket
     if (e == cudaSuccess) e = cudaMallocHost(&c->h_counters, sizeof(unsigned long long) * CNT_N);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->stats_ready, cudaEventDisableTiming);
     for (int i = 0; i < kRing && e == cudaSuccess; ++i) {
         e = cudaEventCreateWithFlags(&c->slot_rendered[i], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->slot_copied[i], cudaEventDisableTiming);
@@ -502,6 +520,7 @@ int pyvr_cuda_destroy(pyvr_ctx *c) {
     cudaFree(c->d_counters);
     if (c->h_counters) cudaFreeHost(c->h_counters);
     for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
+    if (c->stats_ready) cudaEventDestroy(c->stats_ready);
     for (int i = 0; i < kRing; ++i) {
         if (c->slot_rendered[i]) cudaEventDestroy(c->slot_rendered[i]);
         if (c->slot_copied[i]) cudaEventDestroy(c->slot_copied[i]);
@@ -534,6 +553,10 @@ int pyvr_cuda_set_option(pyvr_ctx *c, const char *key, int value) {
     if (!c || !key) return fail(PYVR_ERR_INVALID, "ctx or key is NULL");
     if (strcmp(key, "pair") == 0) {   // takes effect at the next upload
         c->pair_option = value < 0 ? -1 : (value != 0);
+        return PYVR_OK;
+    }
+    if (strcmp(key, "async_device_output") == 0) {   // 1: renders into DEVICE buffers return without a host sync
+        c->async_device = value != 0;
         return PYVR_OK;
     }
     if (strcmp(key, "brick8") == 0) {   // 2x2x2-texel bricks (0 off, 1 on); takes effect at the next upload
@@ -840,6 +863,7 @@ int pyvr_cuda_render_batch(pyvr_ctx *c, const pyvr_view *views, int n, uint8_t *
     DeviceGuard guard(c->device);
     const size_t frame_bytes = frame_pixels(c) * sizeof(uchar4);
     memset(&c->stats, 0, sizeof c->stats);
+    c->stats_pending = false;      // stats of an earlier asynchronous render that nobody asked for
     if (!renderable(c)) {  // cleared framebuffer
         if (out_is_device) {
             CU(cudaMemsetAsync(out, 0, frame_bytes * n, c->stream));
@@ -892,7 +916,7 @@ int pyvr_cuda_render_batch(pyvr_ctx *c, const pyvr_view *views, int n, uint8_t *
         }
         CU(cudaStreamSynchronize(c->copy_stream));
     }
-    return finish_stats(c, pairs, n);
+    return finish_stats(c, pairs, n, c->async_device && out_is_device);
 }
 
 int pyvr_cuda_render(pyvr_ctx *c, uint8_t *out, int out_is_device) {
@@ -917,6 +941,7 @@ int pyvr_cuda_render_accum(pyvr_ctx *c, float *out, int out_is_device) {
     DeviceGuard guard(c->device);
     const size_t bytes = frame_pixels(c) * sizeof(float4);
     memset(&c->stats, 0, sizeof c->stats);
+    c->stats_pending = false;
     if (!renderable(c) || !c->have_view) {
         if (out_is_device) {
             CU(cudaMemsetAsync(out, 0, bytes, c->stream));
@@ -940,7 +965,7 @@ int pyvr_cuda_render_accum(pyvr_ctx *c, float *out, int out_is_device) {
     rc = march(c, 0, 1, nullptr, target, 0);
     if (rc != PYVR_OK) return rc;
     if (!out_is_device) CU(cudaMemcpyAsync(out, c->accum, bytes, cudaMemcpyDeviceToHost, c->stream));
-    return finish_stats(c, 1, 1);
+    return finish_stats(c, 1, 1, c->async_device && out_is_device);
 }
 
 int pyvr_cuda_render_accum_relay(pyvr_ctx *c, const float *in_accum, float *out_accum) {
@@ -949,6 +974,7 @@ int pyvr_cuda_render_accum_relay(pyvr_ctx *c, const float *in_accum, float *out_
     if (c->params.flags & PYVR_FLAG_STRICT) return fail(PYVR_ERR_STATE, "relay rendering is a fast-path feature");
     DeviceGuard guard(c->device);
     memset(&c->stats, 0, sizeof c->stats);
+    c->stats_pending = false;
     int rc = ensure_views(c, 1);
     if (rc == PYVR_OK) rc = ensure_events(c, 1);
     if (rc != PYVR_OK) return rc;
@@ -957,11 +983,14 @@ int pyvr_cuda_render_accum_relay(pyvr_ctx *c, const float *in_accum, float *out_
     c->launch_view = &c->view;
     rc = march(c, 0, 1, nullptr, reinterpret_cast<float4 *>(out_accum), 0, reinterpret_cast<const float4 *>(in_accum));
     if (rc != PYVR_OK) return rc;
-    return finish_stats(c, 1, 1);
+    return finish_stats(c, 1, 1, c->async_device);   // relay buffers are device buffers
 }
 
 int pyvr_cuda_get_stats(pyvr_ctx *c, pyvr_stats *out) {
     if (!c || !out) return fail(PYVR_ERR_INVALID, "NULL argument");
+    DeviceGuard guard(c->device);
+    int rc = resolve_stats(c);
+    if (rc != PYVR_OK) return rc;
     *out = c->stats;
     return PYVR_OK;
 }
@@ -1058,6 +1087,44 @@ int pyvr_cuda_flag_signal(int device, uint32_t *flag, uint32_t value, void *cuda
     if (!flag) return fail(PYVR_ERR_INVALID, "flag is NULL");
     DeviceGuard guard(device);
     CU(launch_flag_signal(flag, value, (cudaStream_t)cuda_stream));
+    return PYVR_OK;
+}
+
+int pyvr_cuda_flag_signal_many(int device, uint32_t *const *flags, int n_flags, uint32_t value, void *cuda_stream) {
+    if (!flags || n_flags < 1) return fail(PYVR_ERR_INVALID, "flags is NULL or empty");
+    for (int i = 0; i < n_flags; ++i)
+        if (!flags[i]) return fail(PYVR_ERR_INVALID, "flags[%d] is NULL", i);
+    DeviceGuard guard(device);
+    CU(launch_flag_signal_many(flags, n_flags, value, (cudaStream_t)cuda_stream));
+    return PYVR_OK;
+}
+
+int pyvr_cuda_binary_swap(int device, const pyvr_swap_round *rounds, int n_rounds, uint32_t value,
+                          float termination_alpha, uint32_t flags, void *cuda_stream) {
+    if (!rounds || n_rounds < 0) return fail(PYVR_ERR_INVALID, "rounds is NULL");
+    for (int r = 0; r < n_rounds; ++r) {
+        const pyvr_swap_round &q = rounds[r];
+        if (!q.front || !q.back || (!q.out && !q.out8)) return fail(PYVR_ERR_INVALID, "round %d: NULL image pointer", r);
+    }
+    DeviceGuard guard(device);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    for (int r = 0; r < n_rounds; ++r) {
+        const pyvr_swap_round &q = rounds[r];
+        if (q.signal_before) CU(launch_flag_signal(q.signal_before, value, st));
+        if (q.wait_flag) CU(launch_flag_wait(q.wait_flag, 1, value, st));
+        if (q.out8)
+            CU(launch_composite_finalize(reinterpret_cast<const float4 *>(q.front), reinterpret_cast<const float4 *>(q.back),
+                                         reinterpret_cast<float4 *>(q.out), reinterpret_cast<uchar4 *>(q.out8), (size_t)q.n_pixels,
+                                         termination_alpha, flags, st));
+        else
+            CU(launch_composite_over(reinterpret_cast<const float4 *>(q.front), reinterpret_cast<const float4 *>(q.back),
+                                     reinterpret_cast<float4 *>(q.out), (size_t)q.n_pixels, termination_alpha, st));
+        unsigned *after[2];
+        int n_after = 0;
+        if (q.signal_done) after[n_after++] = q.signal_done;
+        if (q.signal_next) after[n_after++] = q.signal_next;
+        if (n_after) CU(launch_flag_signal_many(after, n_after, value, st));
+    }
     return PYVR_OK;
 }
 

@@ -144,6 +144,7 @@ cudaError_t launch_composite_finalize(const float4 *front, const float4 *back, f
 // stream-ordered flags in (peer) device memory: signal = system-scope release store, wait = spin until *flag >= value
 cudaError_t launch_flag_signal(unsigned *flag, unsigned value, cudaStream_t stream);
 cudaError_t launch_flag_wait(const unsigned *flags, int n_flags, unsigned value, cudaStream_t stream);
+cudaError_t launch_flag_signal_many(unsigned *const *flags, int n, unsigned value, cudaStream_t stream);   // one launch per 16 flags
 cudaError_t launch_pack_texels(const float *scalar, const float *normals, const VolumeDesc &vol,
                                bool half_texels, cudaStream_t stream);
 // replicate the edge texels of the stored block into the one-texel apron (after every pack / generate)

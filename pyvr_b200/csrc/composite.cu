@@ -69,6 +69,16 @@ __global__ void flag_signal_kernel(unsigned *flag, unsigned value) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(value) : "memory");
 }
 
+struct FlagList {
+    unsigned *flag[16];
+    int n;
+};
+__global__ void flag_signal_many_kernel(FlagList list, unsigned value) {
+    __threadfence_system();
+    if ((int)threadIdx.x < list.n)
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(list.flag[threadIdx.x]), "r"(value) : "memory");
+}
+
 __global__ void flag_wait_kernel(const unsigned *flags, int n_flags, unsigned value) {
     if ((int)threadIdx.x < n_flags) {
         unsigned v;
@@ -112,6 +122,19 @@ cudaError_t launch_composite_finalize(const float4 *front, const float4 *back, f
 cudaError_t launch_flag_signal(unsigned *flag, unsigned value, cudaStream_t stream) {
     flag_signal_kernel<<<1, 1, 0, stream>>>(flag, value);
     return cudaGetLastError();
+}
+
+cudaError_t launch_flag_signal_many(unsigned *const *flags, int n, unsigned value, cudaStream_t stream) {
+    if (n < 0) return cudaErrorInvalidValue;
+    for (int first = 0; first < n; first += 16) {      // one launch per 16 peers
+        FlagList list{};
+        list.n = n - first < 16 ? n - first : 16;
+        for (int i = 0; i < list.n; ++i) list.flag[i] = flags[first + i];
+        flag_signal_many_kernel<<<1, 32, 0, stream>>>(list, value);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
 }
 
 cudaError_t launch_flag_wait(const unsigned *flags, int n_flags, unsigned value, cudaStream_t stream) {

@@ -80,6 +80,8 @@ SYMBOLS = {
     "pyvr_cuda_composite_finalize": (_i, [_i, _vp, _vp, _vp, _vp, _c.c_size_t, _c.c_float, _c.c_uint32, _vp]),
     "pyvr_cuda_flag_signal": (_i, [_i, _vp, _c.c_uint32, _vp]),
     "pyvr_cuda_flag_wait": (_i, [_i, _vp, _i, _c.c_uint32, _vp]),
+    "pyvr_cuda_flag_signal_many": (_i, [_i, _vp, _i, _c.c_uint32, _vp]),
+    "pyvr_cuda_binary_swap": (_i, [_i, _vp, _i, _c.c_uint32, _c.c_float, _c.c_uint32, _vp]),
     "pyvr_cuda_device_alloc": (_i, [_i, _c.c_size_t, _c.POINTER(_vp)]),
     "pyvr_cuda_device_free": (_i, [_i, _vp]),
     "pyvr_cuda_ipc_export": (_i, [_i, _vp, _vp]),
@@ -258,6 +260,24 @@ def composite_finalize(device: int, front_ptr: int, back_ptr: int, accum_out_ptr
 
 def flag_signal(device: int, flag_ptr: int, value: int, stream: int = 0) -> None:
     check(lib().pyvr_cuda_flag_signal(device, _vp(flag_ptr), value & 0xFFFFFFFF, _vp(stream)))
+
+
+def flag_signal_many(device: int, flag_ptrs, value: int, stream: int = 0) -> None:
+    """The same release store to several flags (one per peer) in one launch."""
+    arr = (_vp * len(flag_ptrs))(*[_vp(p) for p in flag_ptrs])
+    check(lib().pyvr_cuda_flag_signal_many(device, arr, len(flag_ptrs), value & 0xFFFFFFFF, _vp(stream)))
+
+
+class SwapRound(_c.Structure):
+    """``pyvr_swap_round`` (include/pyvr_cuda.h): one round of a binary swap, raw device pointers (0 = NULL)."""
+    _fields_ = [("front", _vp), ("back", _vp), ("out", _vp), ("out8", _vp), ("n_pixels", _c.c_uint64),
+                ("signal_before", _vp), ("wait_flag", _vp), ("signal_done", _vp), ("signal_next", _vp)]
+
+
+def binary_swap(device: int, rounds, value: int, termination_alpha: float = 0.99, flags: int = 0, stream: int = 0) -> None:
+    """All rounds of a binary swap enqueued back to back by one C call (``pyvr_cuda_binary_swap``)."""
+    arr = (SwapRound * len(rounds))(*rounds)
+    check(lib().pyvr_cuda_binary_swap(device, arr, len(rounds), value & 0xFFFFFFFF, termination_alpha, flags, _vp(stream)))
 
 
 def flag_wait(device: int, flags_ptr: int, n_flags: int, value: int, stream: int = 0) -> None:

@@ -356,6 +356,13 @@ class CudaVolumeRenderer:
         renderer's own non-blocking stream; pass ``1`` (``cudaStreamLegacy``) for the legacy default stream."""
         _cabi.check(self._lib.pyvr_cuda_set_stream(self._ctx, ctypes.c_void_p(cuda_stream)))
 
+    def set_async_device_output(self, enabled: bool) -> None:
+        """``True``: renders into DEVICE buffers (``render_to_device``, ``render_accum_to_device``, ``render_batch(device_ptr=...)``,
+        relay) return as soon as the work is enqueued -- the pixels are valid in the order of the renderer's stream,
+        and ``stats`` waits for the counters.  Default ``False``: every render call ends with a host synchronisation.
+        The multi-GPU sessions switch it on for the renderer they are bound to."""
+        _cabi.check(self._lib.pyvr_cuda_set_option(self._ctx, b"async_device_output", int(bool(enabled))))
+
     @property
     def stats(self) -> dict:
         """Work counters and device time of the last render call (``pyvr_stats``)."""
