@@ -111,6 +111,7 @@ def measure(args, rank, world, local_rank, workload, steps, warmup, size=None, w
     renderer.set_camera(camera)
     setup_s = time.perf_counter() - t0
 
+    texel_layout = renderer.texel_layout
     frame = torch.zeros((n_pixels, 4), dtype=torch.uint8, device="cuda")
     frame_ptr = frame.data_ptr()
     pinned = _cabi.PinnedBuffer(n_pixels * 4)
@@ -212,6 +213,7 @@ def measure(args, rank, world, local_rank, workload, steps, warmup, size=None, w
             "higher_is_better": True, "scaling": "weak" if c5 else "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": name, "texels": "f16x4 (8 B/voxel)" if texels == "f16" else "f32x4 (16 B/voxel)",
+                       "texel_layout": texel_layout,
                        "l2_policy": f"inputs larger than L2 (packed block {voxels * (8 if texels == 'f16' else 16) / 2 ** 30:.1f} GiB per GPU), no flush",
                        "empty_space_skipping": not args.no_ess,
                        "sampling": "texture unit, hardware trilinear (8-bit weights)" if args.hwtex else "binary32 software trilinear"},

@@ -252,8 +252,16 @@ int pyvr_cuda_stream_synchronize(int device, void *cuda_stream);
 /* --- misc ------------------------------------------------------------------------------------------ */
 /* Tuning knobs (no reference counterpart).  "swizzle": 1 (default) = bank-rotating row/plane padding of the packed
  * texel layout, 0 = aligned rows (for A/B profiling); must be set before pyvr_cuda_upload_volume.  "pair": z-pair
- * entries (-1 auto, 0 off, 1 on; next upload).  "shard_shift", "shard_in_place": see pyvr_cuda_set_pixel_shard. */
+ * entries (-1 auto, 0 off, 1 on; next upload).  "shard_shift", "shard_in_place": see pyvr_cuda_set_pixel_shard.
+ * "brick8": 2x2x2-texel brick layout (-1 auto = f16x4 texels and a volume edge above 0.7 x the frame height, i.e.
+ * sparse rays; 0 off; 1 on; next upload).  "two_samples": f16x4 march with several samples of a run in flight per ray
+ * (-1 auto = the same sparse-ray rule, 0 off, 1 on).
+ * "async_device_output": 1 = renders into device buffers return without a host synchronisation (the pixels are valid
+ * in stream order; pyvr_cuda_get_stats waits for the counters). */
 int pyvr_cuda_set_option(pyvr_ctx *ctx, const char *key, int value);
+/* What is in effect for the loaded volume, automatic choices resolved: "pair", "brick8", "two_samples",
+ * "async_device_output". */
+int pyvr_cuda_get_option(pyvr_ctx *ctx, const char *key, int *value);
 /* Roofline denominators measured on the spot (no reference counterpart; csrc/bandwidth.cu): bytes per second
  * delivered to registers by coalesced 128-bit loads that hit L1 (level 1: the SM load-return path that bounds
  * the march's texel gather) or stream from L2 with L1 bypassed (level 2); level 3: the DRAM rate of a streaming

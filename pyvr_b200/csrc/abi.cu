@@ -80,7 +80,8 @@ struct pyvr_ctx {
     int pending_views = 0;
     cudaEvent_t stats_ready = nullptr;
     const pyvr_view *launch_view = nullptr;   // host copy of the first view of the launch being prepared (row order)
-    int brick8_option = 0;  // 2x2x2-texel bricks (common.cuh): 0 off (default: slower, see choose_layout), 1 on
+    int two_option = -1;    // f16x4 z-pair march two samples at a time: -1 auto (sparse rays expected), 0 off, 1 on
+    int brick8_option = -1; // 2x2x2-texel bricks (common.cuh): -1 auto (f16x4 and sparse rays expected), 0 off, 1 on
     bool use_brick8 = false;
     cudaArray_t tex_array = nullptr;        // PYVR_FLAG_HWTEX: built on first use from the packed texels
     cudaTextureObject_t tex_obj = 0;
@@ -170,16 +171,26 @@ void inverse4_f32(const float *m, float *o) {
     o[15] = (a20 * b03 - a21 * b01 + a22 * b00) * id;
 }
 
-// Layout (common.cuh) for this upload: rows, z-paired if memory allows, or -- option "brick8" -- 2x2x2-texel bricks.
-// Bricks are a measured NEGATIVE result and therefore off unless asked for (profiles/r02_brick8_ab.txt, C4 = 2048^3
-// f16x4 at 2160p, rays 1.2-1.6 voxels apart): they cut the DRAM traffic of a frame from 45.3 GB to 18.9 GB (ncu) and
-// halve the memory, yet the frame takes 9.3-10.1 ms instead of 8.0-8.6 ms.  The row march is DRAM-bound (5.3 TB/s, 65 %
-// busy); the brick march is bound by the L1 misses an SM can keep in flight -- eight 8-byte requests per sample
-// instead of four 16-byte ones, 43 warp-cycles of long-scoreboard stall per issued instruction, DRAM 25 % busy -- and
-// neither more warps (11 CTAs/SM: 9.9 ms) nor L2 / L1 prefetch of the next bricks (11.2-11.5 ms) fills that gap.
-// On C3 (rays 0.6 voxels apart, L1-bound) bricks cost nothing for f32x4 (478 vs 475 Gsamples/s) and 17 % for f16x4.
-void choose_layout(pyvr_ctx *c, const int local[3]) {
-    c->use_brick8 = c->brick8_option > 0;
+// Layout (common.cuh) for this upload.  Dense rays (C3: 512^3 at 1080p, 0.6 voxels between neighbouring rays, L1-bound):
+// rows, z-paired if memory allows.  Sparse rays (C4 / C5: 2048^3 .. 4096^3 f16x4 at 2160p, 1.2-1.6 voxels between
+// rays, every load a DRAM round trip): 2x2x2-texel bricks, marched with several samples in flight per ray.  Sparse =
+// more than about 0.85 voxels between neighbouring rays of a fitted view, i.e. (45 degree field of view, camera three
+// half-extents away) a volume edge above 0.7 x the frame height.  Evidence, C4 on one B200
+// (profiles/r02_brick8_ab.txt, r02_multi_sample_ab.txt, r02_c4_ncu_summary.txt):
+//   rows + z-pairs, one sample in flight     8.0-8.6 ms   45.3 GB of DRAM reads per frame, DRAM 65 % busy
+//   2x2x2 bricks,   one sample in flight     9.3-10.1 ms  18.9 GB, DRAM 25 % busy: latency-bound, prefetch no help
+//   rows + z-pairs, 2-4 samples in flight    6.1-6.8 ms   DRAM-bound again (45 GB at ~7 TB/s)
+//   2x2x2 bricks,   4 samples in flight      3.7 ms       <- the default for this regime; half the memory of z-pairs
+// The brick layout alone was a negative result; what it needed was enough loads in flight per ray to turn its 2.4x
+// lower traffic into time.  f32x4 texels keep the row layouts (no multi-sample path: 32 registers per sample).
+bool sparse_rays_expected(const pyvr_ctx *c, const int g[3]) {
+    const int edge = g[0] > g[1] ? (g[0] > g[2] ? g[0] : g[2]) : (g[1] > g[2] ? g[1] : g[2]);
+    return (double)edge > 0.7 * (double)c->height;
+}
+
+void choose_layout(pyvr_ctx *c, const int local[3], const int global[3]) {
+    c->use_brick8 = c->brick8_option < 0 ? (c->half_texels && sparse_rays_expected(c, global ? global : local))
+                                         : c->brick8_option > 0;
     const size_t doubled = (size_t)local[0] * local[1] * local[2] * (c->half_texels ? 8 : 16) * 2;
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) free_b = 0;   // called after the old volume was freed
@@ -191,7 +202,7 @@ void choose_layout(pyvr_ctx *c, const int local[3]) {
 void fill_volume_desc(pyvr_ctx *c, const int local[3], const int global[3], const int org[3],
                       const int own_lo[3], const int own_hi[3], const float bmin[3], const float bmax[3]) {
     VolumeDesc &v = c->vol;
-    choose_layout(c, local);
+    choose_layout(c, local, global);
     v.bricked = global != nullptr;
     for (int a = 0; a < 3; ++a) {
         v.n[a] = local[a];
@@ -360,6 +371,8 @@ MarchArgs make_args(const pyvr_ctx *c) {
     a.shard_count = c->shard_count;
     a.shard_shift = c->shard_shift;
     a.tile_counter = reinterpret_cast<unsigned *>(c->d_counters + CNT_N);
+    // several samples in flight per lane pay off when the rays are sparse (choose_layout); on C3 f16x4 they cost 2x
+    a.two_samples = c->two_option < 0 ? sparse_rays_expected(c, c->vol.gn) : c->two_option;
     return a;
 }
 
@@ -479,6 +492,8 @@ int pyvr_cuda_create(int device, int width, int height, pyvr_ctx **out_ctx) {
     if (layout) c->swizzle = strcmp(layout, "linear") != 0;   // "linear" = no swizzle, anything else = default
     const char *pair = getenv("PYVR_CUDA_PAIR");
     if (pair) c->pair_option = atoi(pair);
+    const char *two = getenv("PYVR_CUDA_TWO_SAMPLES");
+    if (two) c->two_option = atoi(two);
     const char *b8 = getenv("PYVR_CUDA_BRICK8");
     if (b8) c->brick8_option = atoi(b8);
     // defaults of the reference renderer: balanced preset, Light.default(), bounds +-0.5
@@ -549,6 +564,19 @@ int pyvr_cuda_set_stream(pyvr_ctx *c, void *cuda_stream) {
     return PYVR_OK;
 }
 
+int pyvr_cuda_get_option(pyvr_ctx *c, const char *key, int *value) {
+    if (!c || !key || !value) return fail(PYVR_ERR_INVALID, "NULL argument");
+    // what is in effect for the volume that is loaded now (the automatic choices resolved)
+    if (strcmp(key, "pair") == 0) *value = c->have_volume ? c->vol.pair : 0;
+    else if (strcmp(key, "brick8") == 0) *value = c->have_volume ? c->vol.brick8 : 0;
+    else if (strcmp(key, "two_samples") == 0)
+        *value = c->have_volume && c->half_texels && (c->vol.pair || c->vol.brick8) &&
+                 (c->two_option < 0 ? sparse_rays_expected(c, c->vol.gn) : c->two_option != 0);
+    else if (strcmp(key, "async_device_output") == 0) *value = c->async_device;
+    else return fail(PYVR_ERR_INVALID, "unknown option '%s'", key);
+    return PYVR_OK;
+}
+
 int pyvr_cuda_set_option(pyvr_ctx *c, const char *key, int value) {
     if (!c || !key) return fail(PYVR_ERR_INVALID, "ctx or key is NULL");
     if (strcmp(key, "pair") == 0) {   // takes effect at the next upload
@@ -559,8 +587,12 @@ int pyvr_cuda_set_option(pyvr_ctx *c, const char *key, int value) {
         c->async_device = value != 0;
         return PYVR_OK;
     }
-    if (strcmp(key, "brick8") == 0) {   // 2x2x2-texel bricks (0 off, 1 on); takes effect at the next upload
-        c->brick8_option = value > 0;
+    if (strcmp(key, "two_samples") == 0) {   // f16x4 z-pair march, two samples per iteration (-1 auto, 0 off, 1 on)
+        c->two_option = value < 0 ? -1 : (value != 0);
+        return PYVR_OK;
+    }
+    if (strcmp(key, "brick8") == 0) {   // 2x2x2-texel bricks (-1 auto, 0 off, 1 on); takes effect at the next upload
+        c->brick8_option = value < 0 ? -1 : (value != 0);
         return PYVR_OK;
     }
     if (strcmp(key, "shard_shift") == 0) {      // tile-group edge of the image-space sharding, in CTA tiles (log2)

@@ -27,10 +27,11 @@ namespace pyvr {
 //   * optional Z-PAIR entries (pair = 1): entry(ix, iy, iz) = {texel(iz), texel(iz + 1)} (2x memory): one 256-bit
 //     (f32x4) / 128-bit (f16x4) load fetches both z-taps of a corner row.
 //   entry index (ix, iy, iz) = (ix + 1) * pitch_x + (iy + 1) * pitch_y + (iz + 1),   ix in [-1, n[0]] etc.
-//   * BRICK8 (option "brick8", off by default; never with z-pairs): the array, apron included, is cut into
-//     2x2x2-texel bricks, one brick = 8 consecutive texels = 64 bytes (f16x4) or 128 bytes (f32x4), so that a plane of
-//     samples cuts the fewest DRAM accesses whatever the view direction.  It does what it was built for -- 2.4x less
-//     DRAM traffic on C4 -- and is still slower there than z-paired rows (abi.cu, choose_layout).  With X = ix + 1 etc.:
+//   * BRICK8 (f16x4 volumes whose rays will be sparse -- C4 / C5 -- or option "brick8"; never with z-pairs): the
+//     array, apron included, is cut into 2x2x2-texel bricks, one brick = 8 consecutive texels = 64 bytes (f16x4: one
+//     DRAM access) or 128 bytes (f32x4), so that a plane of samples cuts the fewest DRAM accesses whatever the view
+//     direction: 2.4x less DRAM traffic than z-paired rows on C4, which the march turns into time by keeping several
+//     samples in flight per ray (abi.cu, choose_layout; march.cu, LAYOUT 4).  With X = ix + 1 etc.:
 //   entry index = (((X >> 1) * pitch_x + (Y >> 1) * pitch_y + (Z >> 1)) << 3) | (X & 1) << 2 | (Y & 1) << 1 | (Z & 1)
 //     with pitch_y = bricks per z-row, pitch_x = bricks per x-plane.
 struct VolumeDesc {
@@ -107,6 +108,7 @@ struct MarchArgs {
     // asked for in-place sharding into a frame that all ranks write).  shard_count <= 1: everything.
     int shard_rank, shard_count, shard_shift;
     int n_views;                   // views of this launch (filled by the launcher)
+    int two_samples;               // f16x4 march: several samples of a run in flight per lane (sparse rays; LAYOUT 3 / 4)
     int first_row;                 // tile row dispatched first (the rows follow from it outwards); -1 = natural order
     unsigned *tile_counter;        // PYVR_PERSISTENT builds: ticket counter of the tile queue (zeroed per launch)
 };

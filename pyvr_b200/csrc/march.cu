@@ -124,6 +124,14 @@ __device__ __forceinline__ void load_row(const char *p, Texel2 &lo, Texel2 &hi) 
     }
 }
 
+// f16x4 z-pair entry, raw: the 16 bytes of one corner row, converted when the sample is filtered (PAIRED samples below
+// keep a second sample's four rows in flight in this form: 16 registers instead of 32).
+__device__ __forceinline__ uint4 load_row_raw(const char *p) { return __ldg(reinterpret_cast<const uint4 *>(p)); }
+__device__ __forceinline__ void unpack_row(const uint4 &raw, Texel2 &lo, Texel2 &hi) {
+    lo.sn = half2_to_f32x2(raw.x); lo.yz = half2_to_f32x2(raw.y);
+    hi.sn = half2_to_f32x2(raw.z); hi.yz = half2_to_f32x2(raw.w);
+}
+
 // One texel (brick8 layout): LDG.64 (f16x4) or LDG.128 (f32x4).
 template <bool HALF>
 __device__ __forceinline__ void load_one(const char *p, Texel2 &t) {
@@ -312,6 +320,16 @@ __device__ __forceinline__ void index_slab(float X0, float D, float lo, float hi
 #ifndef PYVR_PF_LEVEL
 #define PYVR_PF_LEVEL 2
 #endif
+// LAYOUT 3 / 4 (f16x4, sparse rays): samples of a run in flight per lane, and the occupancy that leaves room for their
+// raw texels (16 registers per sample).  Measured on C4 with 2x2x2 bricks (profiles/r02_multi_sample_ab.txt): one
+// sample 9.4 ms per frame; K = 2 at 5 CTAs/SM 5.35; K = 3 at 4 CTAs/SM 4.38; K = 4 at 3 CTAs/SM 3.69; K = 5, 6, 8 at
+// 3 or 2 CTAs/SM 3.69-3.72 (DRAM: 18.9 GB per frame).  Spilling variants lose everything (K = 2 at 7-9 CTAs/SM: 9.5-12.7).
+#ifndef PYVR_TWO_K
+#define PYVR_TWO_K 4
+#endif
+#ifndef PYVR_MARCH_MIN_BLOCKS_TWO
+#define PYVR_MARCH_MIN_BLOCKS_TWO 3   // up to 168 registers; K = 4 uses 148, no spills
+#endif
 #ifndef PYVR_B8_PF_DIST
 #define PYVR_B8_PF_DIST 0   // brick8 layout: prefetch the bricks of the sample this many steps ahead (0 = off)
 #endif
@@ -340,11 +358,24 @@ constexpr int MAX_IV = PYVR_MAX_IV;   // active-interval table entries per ray (
                                        // 48 warps per SM (measured: 7 -> 699, 10 -> 890, 12 -> 939, 14 -> 583 Gsamples/s on C3)
 #endif
 
-// LAYOUT: 0 = rows, 1 = rows of z-pair entries, 2 = 2x2x2-texel bricks (common.cuh)
+// LAYOUT: 0 = rows, 1 = rows of z-pair entries, 2 = 2x2x2-texel bricks (common.cuh), 3 = z-pair entries marched two
+// samples at a time (f16x4 only; MarchArgs.two_samples)
 template <bool STRICT, bool HALF, typename IDX, bool BRICK, int LAYOUT, bool TEX>
-__global__ void __launch_bounds__(CTA_THREADS, TEX ? PYVR_MARCH_MIN_BLOCKS_TEX : (HALF && !STRICT) ? PYVR_MARCH_MIN_BLOCKS_F16 : PYVR_MARCH_MIN_BLOCKS)
+__global__ void __launch_bounds__(CTA_THREADS, TEX ? PYVR_MARCH_MIN_BLOCKS_TEX : LAYOUT >= 3 ? PYVR_MARCH_MIN_BLOCKS_TWO
+                                                   : (HALF && !STRICT) ? PYVR_MARCH_MIN_BLOCKS_F16 : PYVR_MARCH_MIN_BLOCKS)
 march_kernel(const __grid_constant__ MarchArgs a) {
-    constexpr bool PAIR = LAYOUT == 1;
+    constexpr bool PAIR = LAYOUT == 1 || LAYOUT == 3;
+    // Several samples per iteration (f16x4, the format of the 2048^3 / 4096^3 configs): with sparse rays every warp
+    // sits on its loads for a DRAM round trip (ncu on C4: 52 warp-cycles of long-scoreboard stall per issued
+    // instruction, issue slots 14 % busy), and the longest ray alone bounds a sharded launch.  Requesting the texels of
+    // samples i .. i+K-1 of a run together multiplies the loads in flight per lane and divides the round trips of a
+    // ray; the samples are still composited in order, and those after the one that saturates the ray are dropped, so
+    // the arithmetic -- and every pixel -- is unchanged (test_two_samples_per_iteration_is_bit_identical).
+    // Chosen per launch (launch_march): on C3, where the L1 data stage binds, the extra registers cost more than the
+    // round trips save.
+    constexpr bool TWO = LAYOUT == 3;
+    constexpr bool TWO_B8 = LAYOUT == 4;       // the same for the 2x2x2-brick layout
+    static_assert(!(TWO || TWO_B8) || (HALF && !STRICT && !TEX), "multi-sample march: f16x4 fast path only");
     constexpr int TEXEL_BYTES = HALF ? 8 : 16, ENTRY_BYTES = TEXEL_BYTES << (PAIR ? 1 : 0);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // lane -> pixel inside the warp's 8x4 tile.  The L1 data stage serves a warp-wide load quarter-warp by
@@ -686,7 +717,55 @@ march_kernel(const __grid_constant__ MarchArgs a) {
                     const float wx = x - (float)ix, wy = y - (float)iy, wz = z - (float)iz;
                     Texel2 c000, c001, c010, c011, c100, c101, c110, c111;
                     bool fetch = true;
-                    if constexpr (LAYOUT == 2) {
+                    if constexpr (TWO_B8) {
+                        // 2x2x2-texel bricks, K samples of the run in flight: eight single-texel loads per sample, raw
+                        constexpr int K = PYVR_TWO_K;
+                        const int cnt = min(K, run_end - i);
+                        uint2 raw[K][8];
+                        float wgt[K][3];
+#pragma unroll
+                        for (int k = 0; k < K; ++k) {
+                            if (k < cnt) {
+                                const float fk = fi + (float)k;
+                                const float xk = fmaf(fk, DX, X0), yk = fmaf(fk, DY, Y0), zk = fmaf(fk, DZ, Z0);
+                                const int jx = __float2int_rd(xk), jy = __float2int_rd(yk), jz = __float2int_rd(zk);
+                                wgt[k][0] = xk - (float)jx; wgt[k][1] = yk - (float)jy; wgt[k][2] = zk - (float)jz;
+                                const int X = jx - ogx + 1, Y = jy - ogy + 1, Z = jz - ogz + 1;
+                                const IDX ex0 = (IDX)(X >> 1) * PX8 + (IDX)((X & 1) << 2), ex1 = (IDX)((X + 1) >> 1) * PX8 + (IDX)(((X + 1) & 1) << 2);
+                                const IDX ey0 = (IDX)(Y >> 1) * PY8 + (IDX)((Y & 1) << 1), ey1 = (IDX)((Y + 1) >> 1) * PY8 + (IDX)(((Y + 1) & 1) << 1);
+                                const IDX ez0 = (IDX)((Z >> 1) << 3) + (IDX)(Z & 1), ez1 = (IDX)(((Z + 1) >> 1) << 3) + (IDX)((Z + 1) & 1);
+                                const IDX e4[4] = {ex0 + ey0, ex0 + ey1, ex1 + ey0, ex1 + ey1};
+#pragma unroll
+                                for (int c = 0; c < 4; ++c) {
+                                    raw[k][2 * c] = __ldg(reinterpret_cast<const uint2 *>(a.tap_base + (long long)(e4[c] + ez0) * TEXEL_BYTES));
+                                    raw[k][2 * c + 1] = __ldg(reinterpret_cast<const uint2 *>(a.tap_base + (long long)(e4[c] + ez1) * TEXEL_BYTES));
+                                }
+                            }
+                        }
+                        auto filter_shade = [&](const uint2 (&q)[8], const float (&f)[3]) -> bool {
+                            const f32x2 tz2 = pack2(f[2], f[2]), ty2 = pack2(f[1], f[1]), tx2 = pack2(f[0], f[0]);
+                            f32x2 sn[4], yz[4];
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) {     // z-lerp of corner row c = (x tap, y tap)
+                                sn[c] = lerp2(half2_to_f32x2(q[2 * c].x), half2_to_f32x2(q[2 * c + 1].x), tz2);
+                                yz[c] = lerp2(half2_to_f32x2(q[2 * c].y), half2_to_f32x2(q[2 * c + 1].y), tz2);
+                            }
+                            float density, nx, ny, nz;
+                            unpack2(lerp2(lerp2(sn[0], sn[1], ty2), lerp2(sn[2], sn[3], ty2), tx2), density, nx);
+                            unpack2(lerp2(lerp2(yz[0], yz[1], ty2), lerp2(yz[2], yz[3], ty2), tx2), ny, nz);
+                            return shade_fast(a, s_lut, density, nx, ny, nz, acc);
+                        };
+                        visible = filter_shade(raw[0], wgt[0]);
+                        fetch = false;
+#pragma unroll
+                        for (int k = 1; k < K; ++k) {
+                            if (k < cnt && acc.a < a.term_alpha) {      // volume.frag.glsl:87: alpha is tested before every sample
+                                ++i;
+                                ++n_fetched;
+                                visible |= filter_shade(raw[k], wgt[k]);
+                            }
+                        }
+                    } else if constexpr (LAYOUT == 2) {
                         // 2x2x2-texel bricks: per axis the brick term and the in-brick bit of the lower and the upper tap
                         // (coordinates shifted by the apron), then eight single-texel loads.
                         const int X = ix - ogx + 1, Y = iy - ogy + 1, Z = iz - ogz + 1;
@@ -719,6 +798,57 @@ march_kernel(const __grid_constant__ MarchArgs a) {
                             prefetch_line(a.tap_base + (long long)(qx0 + qy1 + qz1) * TEXEL_BYTES);
                         }
 #endif
+                    } else {
+                    if constexpr (TWO) {
+                        // the rows of samples i .. i + K - 1 of the run are requested now (raw: 16 registers per sample)
+                        // and filtered one after the other
+                        constexpr int K = PYVR_TWO_K;
+                        const int cnt = min(K, run_end - i);
+                        uint4 raw[K][4];
+                        float wgt[K][3];
+#pragma unroll
+                        for (int k = 0; k < K; ++k) {
+                            if (k < cnt) {
+                                const float fk = fi + (float)k;
+                                const float xk = fmaf(fk, DX, X0), yk = fmaf(fk, DY, Y0), zk = fmaf(fk, DZ, Z0);
+                                const int jx = __float2int_rd(xk), jy = __float2int_rd(yk), jz = __float2int_rd(zk);
+                                wgt[k][0] = xk - (float)jx; wgt[k][1] = yk - (float)jy; wgt[k][2] = zk - (float)jz;
+                                const IDX ek = (IDX)(jx - ogx) * (IDX)vol.pitch_x + (IDX)(jy - ogy) * (IDX)vol.pitch_y + (IDX)(jz - ogz);
+                                const char *q00 = a.tap_base + (long long)ek * ENTRY_BYTES;
+                                raw[k][0] = load_row_raw(q00); raw[k][1] = load_row_raw(q00 + a.stride_y);
+                                raw[k][2] = load_row_raw(q00 + a.stride_x); raw[k][3] = load_row_raw(q00 + a.stride_x + a.stride_y);
+                            }
+                        }
+                        // z-lerp each corner row as it is unpacked (8 live values per row, not 32 per sample), then y, then x:
+                        // the same operations in the same order as the one-sample path
+                        auto filter_shade = [&](const uint4 (&q)[4], const float (&f)[3]) -> bool {
+                            const f32x2 tz2 = pack2(f[2], f[2]), ty2 = pack2(f[1], f[1]), tx2 = pack2(f[0], f[0]);
+                            Texel2 lo, hi;
+                            unpack_row(q[0], lo, hi);
+                            const f32x2 a00 = lerp2(lo.sn, hi.sn, tz2), b00 = lerp2(lo.yz, hi.yz, tz2);
+                            unpack_row(q[1], lo, hi);
+                            const f32x2 a01 = lerp2(lo.sn, hi.sn, tz2), b01 = lerp2(lo.yz, hi.yz, tz2);
+                            unpack_row(q[2], lo, hi);
+                            const f32x2 a10 = lerp2(lo.sn, hi.sn, tz2), b10 = lerp2(lo.yz, hi.yz, tz2);
+                            unpack_row(q[3], lo, hi);
+                            const f32x2 a11 = lerp2(lo.sn, hi.sn, tz2), b11 = lerp2(lo.yz, hi.yz, tz2);
+                            float density, nx, ny, nz;
+                            unpack2(lerp2(lerp2(a00, a01, ty2), lerp2(a10, a11, ty2), tx2), density, nx);
+                            unpack2(lerp2(lerp2(b00, b01, ty2), lerp2(b10, b11, ty2), tx2), ny, nz);
+                            return shade_fast(a, s_lut, density, nx, ny, nz, acc);
+                        };
+                        visible = filter_shade(raw[0], wgt[0]);
+                        fetch = false;                         // all K samples are handled here
+#pragma unroll
+                        for (int k = 1; k < K; ++k) {
+                            // the shader tests alpha before every sample (volume.frag.glsl:87): once the ray is saturated the
+                            // samples already requested are dropped
+                            if (k < cnt && acc.a < a.term_alpha) {
+                                ++i;
+                                ++n_fetched;
+                                visible |= filter_shade(raw[k], wgt[k]);
+                            }
+                        }
                     } else {
                     const IDX e = (IDX)(ix - ogx) * (IDX)vol.pitch_x + (IDX)(iy - ogy) * (IDX)vol.pitch_y + (IDX)(iz - ogz);
                     const char *p00 = a.tap_base + (long long)e * ENTRY_BYTES;
@@ -765,6 +895,7 @@ march_kernel(const __grid_constant__ MarchArgs a) {
                     }
 #endif
                     }   // fetch
+                    }   // one sample per iteration
                     }   // row layouts
                     if (fetch) {
                     // filter order of the oracle: z (memory-fastest) first, then y, then x; {s, nx} and {ny, nz} packed
@@ -884,8 +1015,10 @@ cudaError_t launch_march(const MarchArgs &a, int n_views, bool half_texels, bool
     // 2x2x2 bricks multiply pitches by 8 before the index type is chosen: keep 32-bit indices to a quarter of the range
     if (layout == 2) {
         const bool wide = wide_index || (long long)((a.vol.n[0] + 3) >> 1) * a.vol.pitch_x * 8 >= (1LL << 30);
+        if (half_texels && a.two_samples) return launch_fast<true, 4>(a, n_views, wide, stream);
         return half_texels ? launch_fast<true, 2>(a, n_views, wide, stream) : launch_fast<false, 2>(a, n_views, wide, stream);
     }
+    if (half_texels && layout == 1 && a.two_samples) return launch_fast<true, 3>(a, n_views, wide_index, stream);
     if (half_texels) return layout == 1 ? launch_fast<true, 1>(a, n_views, wide_index, stream)
                                         : launch_fast<true, 0>(a, n_views, wide_index, stream);
     return layout == 1 ? launch_fast<false, 1>(a, n_views, wide_index, stream)

@@ -90,6 +90,7 @@ SYMBOLS = {
     "pyvr_cuda_memcpy": (_i, [_i, _vp, _vp, _c.c_size_t, _i, _vp]),
     "pyvr_cuda_stream_synchronize": (_i, [_i, _vp]),
     "pyvr_cuda_set_option": (_i, [_vp, _c.c_char_p, _i]),
+    "pyvr_cuda_get_option": (_i, [_vp, _c.c_char_p, _c.POINTER(_i)]),
     "pyvr_cuda_measure_cache_bandwidth": (_i, [_i, _i, _c.POINTER(_c.c_double)]),
     "pyvr_cuda_host_alloc": (_i, [_c.c_size_t, _c.POINTER(_vp)]),
     "pyvr_cuda_host_free": (_i, [_vp]),

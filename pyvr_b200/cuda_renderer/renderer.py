@@ -356,6 +356,16 @@ class CudaVolumeRenderer:
         renderer's own non-blocking stream; pass ``1`` (``cudaStreamLegacy``) for the legacy default stream."""
         _cabi.check(self._lib.pyvr_cuda_set_stream(self._ctx, ctypes.c_void_p(cuda_stream)))
 
+    @property
+    def texel_layout(self) -> str:
+        """Layout of the packed texels of the loaded volume and how the march walks it (automatic choices resolved)."""
+        def get(key):
+            v = ctypes.c_int(0)
+            _cabi.check(self._lib.pyvr_cuda_get_option(self._ctx, key, ctypes.byref(v)))
+            return v.value
+        base = "2x2x2-texel bricks" if get(b"brick8") else "rows of z-pair entries" if get(b"pair") else "rows"
+        return base + (", several samples in flight per ray" if get(b"two_samples") else "")
+
     def set_async_device_output(self, enabled: bool) -> None:
         """``True``: renders into DEVICE buffers (``render_to_device``, ``render_accum_to_device``, ``render_batch(device_ptr=...)``,
         relay) return as soon as the work is enqueued -- the pixels are valid in the order of the renderer's stream,

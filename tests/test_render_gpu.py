@@ -222,8 +222,9 @@ def test_brick8_layout_is_bit_identical(texel_format, shape):
     lut = build_rgba_lut(ColorTransferFunction.from_colormap("viridis"), OpacityTransferFunction.linear(0.0, 0.2))
     for strict in (False, True):
         out = {}
-        for b8 in ("0", "1"):
-            os.environ["PYVR_CUDA_BRICK8"] = b8
+        for b8 in ("0", "1", "1+multi"):        # "1+multi": bricks marched with several samples in flight (f16 only)
+            os.environ["PYVR_CUDA_BRICK8"] = b8[0]
+            os.environ["PYVR_CUDA_TWO_SAMPLES"] = "1" if b8.endswith("multi") else "0"
             try:
                 with VolumeRenderer(160, 96, config=RenderConfig.balanced(), light=Light.directional([1, -1, 0]),
                                     texel_format=texel_format, strict=strict) as r:
@@ -232,8 +233,35 @@ def test_brick8_layout_is_bit_identical(texel_format, shape):
                     r.set_lut(lut)
                     out[b8] = r.render_accum()
             finally:
-                del os.environ["PYVR_CUDA_BRICK8"]
+                del os.environ["PYVR_CUDA_BRICK8"], os.environ["PYVR_CUDA_TWO_SAMPLES"]
         assert np.array_equal(out["0"].view(np.uint32), out["1"].view(np.uint32)), (texel_format, shape, strict)
+        assert np.array_equal(out["0"].view(np.uint32), out["1+multi"].view(np.uint32)), (texel_format, shape, strict)
+
+
+@pytest.mark.parametrize("ess", [False, True])
+def test_two_samples_per_iteration_is_bit_identical(c1, ess):
+    """f16x4 z-pair march with two samples of a run in flight per ray (option "two_samples", automatic for large
+    volumes): same samples, same order, the second one dropped when the first saturates the ray -- same floats.
+    The opaque step transfer function makes many rays stop early, on odd and even sample indices."""
+    vol, light, _ = c1
+    luts = [viridis_lut(0.0, 0.3),
+            build_rgba_lut(ColorTransferFunction.from_colormap("viridis"), OpacityTransferFunction.one_step(0.3, 0.0, 0.9))]
+    for lut in luts:
+        out = {}
+        for two in ("0", "1"):
+            os.environ["PYVR_CUDA_TWO_SAMPLES"] = two
+            try:
+                with VolumeRenderer(320, 200, config=RenderConfig.high_quality(), light=light, texel_format="f16",
+                                    empty_space_skipping=ess) as r:
+                    r.load_volume(vol)
+                    r.set_camera(turntable_camera(211))
+                    r.set_lut(lut)
+                    out[two] = (r.render_accum(), r.stats)
+            finally:
+                del os.environ["PYVR_CUDA_TWO_SAMPLES"]
+        assert np.array_equal(out["0"][0].view(np.uint32), out["1"][0].view(np.uint32))
+        for key in ("samples", "rays_hit", "rays_terminated"):
+            assert out["0"][1][key] == out["1"][1][key], key
 
 
 def test_render_without_volume_or_camera_returns_cleared_frame():
