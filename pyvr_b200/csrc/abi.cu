@@ -371,8 +371,11 @@ MarchArgs make_args(const pyvr_ctx *c) {
     a.shard_count = c->shard_count;
     a.shard_shift = c->shard_shift;
     a.tile_counter = reinterpret_cast<unsigned *>(c->d_counters + CNT_N);
-    // several samples in flight per lane pay off when the rays are sparse (choose_layout); on C3 f16x4 they cost 2x
-    a.two_samples = c->two_option < 0 ? sparse_rays_expected(c, c->vol.gn) : c->two_option;
+    // several samples in flight per lane pay off when the rays are sparse (choose_layout) -- on C3 f16x4 they cost 2x --
+    // and when most rays of the launch have work: a sort-last brick is crossed by a fraction of the rays, the rest only
+    // pay for set-up, and 3 CTAs per SM instead of 9 then cost more than the deeper rays gain (C5 on 8 GPUs, march of
+    // the slowest rank: 0.44 -> 0.54 ms; profiles/r02_c5_layout_ab.txt)
+    a.two_samples = c->two_option < 0 ? (sparse_rays_expected(c, c->vol.gn) && !c->vol.bricked) : c->two_option;
     return a;
 }
 
@@ -571,7 +574,7 @@ int pyvr_cuda_get_option(pyvr_ctx *c, const char *key, int *value) {
     else if (strcmp(key, "brick8") == 0) *value = c->have_volume ? c->vol.brick8 : 0;
     else if (strcmp(key, "two_samples") == 0)
         *value = c->have_volume && c->half_texels && (c->vol.pair || c->vol.brick8) &&
-                 (c->two_option < 0 ? sparse_rays_expected(c, c->vol.gn) : c->two_option != 0);
+                 (c->two_option < 0 ? (sparse_rays_expected(c, c->vol.gn) && !c->vol.bricked) : c->two_option != 0);
     else if (strcmp(key, "async_device_output") == 0) *value = c->async_device;
     else return fail(PYVR_ERR_INVALID, "unknown option '%s'", key);
     return PYVR_OK;
