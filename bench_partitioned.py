@@ -201,6 +201,20 @@ def measure(args, rank, world, local_rank, workload, steps, warmup, size=None, w
         sm_mhz = clocks.summary().get("sm_mhz") or 1965.0
         l1_peak = 148 * 128 * sm_mhz * 1e6 / 1e9
         voxels = float(np.prod(stored))
+        # DRAM bytes one whole C4 frame moves (committed ncu capture of the same layout), for the 1-GPU roofline
+        traffic = dram = None
+        if not c5 and world == 1 and not args.hwtex:
+            try:
+                table = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r02_traffic.json")))
+                key = ("bricks_four_in_flight" if "several" in texel_layout else "bricks_one_sample") if "bricks" in texel_layout \
+                    else "rows_zpairs_one_sample"
+                traffic = float(table["c4_dram_bytes_per_frame"][key])
+                dram = {"achieved": traffic / (launch_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                        "frac": traffic / (launch_ms * 1e-3) / 1e9 / peak,
+                        "note": f"DRAM traffic ncu measured for one frame of this layout ({key}, profiles/r02_traffic.json) / kernel time: "
+                                "the binding unit of the sparse-ray march"}
+            except Exception:
+                traffic = dram = None
         name = (f"C5: synthetic {args.size}^3 f16 scalar+normal double_sphere generated on device, {world} sort-last bricks "
                 f"of {stored[0]}x{stored[1]}x{stored[2]} (+1 ghost), {width}x{height}, high_quality, binary swap ({args.exchange}) "
                 "over NVLink, isometric view" if c5 else
@@ -225,7 +239,7 @@ def measure(args, rank, world, local_rank, workload, steps, warmup, size=None, w
                     "frame_nonzero_alpha_pixels": nonzero},
             "gpu_launches": int(args.steps * world),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "march_kernel<fast>",
+                         "traffic": traffic, "dram": dram, "peak_source": peak_src, "kernel": "march_kernel<fast>",
                          "kernel_ms_per_launch": launch_ms, "algorithmic_bytes_per_sample": bytes_per_sample,
                          "march_share_of_step": march_ms / ms,
                          "l1": {"achieved": achieved, "peak": l1_peak, "unit": "GB/s", "frac": achieved / l1_peak},

@@ -189,7 +189,9 @@ bool sparse_rays_expected(const pyvr_ctx *c, const int g[3]) {
 }
 
 void choose_layout(pyvr_ctx *c, const int local[3], const int global[3]) {
-    c->use_brick8 = c->brick8_option < 0 ? (c->half_texels && sparse_rays_expected(c, global ? global : local))
+    // sort-last bricks (global != NULL) are marched one sample at a time (make_args), and then a sample is cheaper as
+    // four 16-byte requests than as eight 8-byte ones: C5 on 8 GPUs 0.96 ms per frame with z-paired rows, 1.03 with bricks
+    c->use_brick8 = c->brick8_option < 0 ? (c->half_texels && !global && sparse_rays_expected(c, local))
                                          : c->brick8_option > 0;
     const size_t doubled = (size_t)local[0] * local[1] * local[2] * (c->half_texels ? 8 : 16) * 2;
     size_t free_b = 0, total_b = 0;
