@@ -220,10 +220,10 @@ void fill_volume_desc(pyvr_ctx *c, const int local[3], const int global[3], cons
         v.ncell[a] = (v.n[a] + kCell - 1) / kCell;
     }
     // padded pitches (common.cuh): rows of n[2] + 2 entries, planes of n[1] + 2 rows, rounded up to the residue
-    // that rotates the L1 bank of texel (ix, iy, iz) by 3*ix + iy entries.  All 16 residue pairs were measured on
-    // C3 with z-pair entries (4 per line; profiles/r02_layout_ab.txt): no rotation 320 Gsamples/s, (1,3) -- the
-    // round-1 slot swizzle -- 428, (3,1) 449; what matters is that the texels one quarter-warp touches -- a short
-    // run along the image-row direction -- spread over the banks.
+    // that rotates the L1 slot of texel (ix, iy, iz) by rx*ix + ry*iy entries.  Measured on C3 with z-pair entries (4
+    // per line) over the whole turntable (profiles/r02_turntable_ab.txt): no rotation 356 Gsamples/s; with 4x1-pixel
+    // passes every odd/odd pair 459; with the shipped 2x2-pixel passes (march.cu, PYVR_LANE_ARR) (3,2) 473, (2,1) 470,
+    // (3,1) 455.  What matters is that the texels the four lanes of a pass touch land in different slots.
     v.pair = c->use_pair ? 1 : 0;
     v.brick8 = c->use_brick8 ? 1 : 0;
     if (v.brick8) {   // pitches count bricks; the apron is part of the bricked array
@@ -232,7 +232,7 @@ void fill_volume_desc(pyvr_ctx *c, const int local[3], const int global[3], cons
         return;
     }
     const int slots = 128 / entry_bytes(c->half_texels, v.pair);
-    int rx = 3, ry = 1;
+    int rx = 3, ry = 2;
     if (!c->swizzle) rx = ry = 0;
     else {
         const char *env = getenv("PYVR_CUDA_SWZ");   // "x,y" override for experiments

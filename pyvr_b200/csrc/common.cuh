@@ -18,12 +18,12 @@ namespace pyvr {
 //     lower tap floor(x) ranges over [-1, n-1] and the upper tap is always lower + 1, so the fast march needs no
 //     index clamps and the four (x, y) corner rows of a sample sit at fixed distances from the first one;
 //   * PADDED PITCHES: one entry = one texel (or one z-pair, below); a row of entries along z is pitch_y entries
-//     long, an x-plane pitch_x entries, with pitch_y = 1 and pitch_x = 3 modulo S = 128 / entry_bytes.  One
+//     long, an x-plane pitch_x entries, with pitch_y = 2 and pitch_x = 3 modulo S = 128 / entry_bytes.  One
 //     warp-wide corner load touches a small planar patch of texels, typically many (x, y) rows at the same z;
 //     with aligned rows they would all sit at the same offset of different 128-byte lines, i.e. on the same L1
 //     data banks, and the load would serialise (measured in round 1: 18.6 data-stage wavefronts per LDG.128, L1
 //     data pipe 99 % busy; 7.9 with the rotation).  The padding rotates the bank of texel (ix, iy, iz) by
-//     (3*ix + iy) entries -- what round 1 did with a slot swizzle -- without a single instruction in the march;
+//     (3*ix + 2*iy) entries -- what round 1 did with a slot swizzle -- without a single instruction in the march;
 //   * optional Z-PAIR entries (pair = 1): entry(ix, iy, iz) = {texel(iz), texel(iz + 1)} (2x memory): one 256-bit
 //     (f32x4) / 128-bit (f16x4) load fetches both z-taps of a corner row.
 //   entry index (ix, iy, iz) = (ix + 1) * pitch_x + (iy + 1) * pitch_y + (iz + 1),   ix in [-1, n[0]] etc.

@@ -309,7 +309,8 @@ __device__ __forceinline__ void index_slab(float X0, float D, float lo, float hi
 #define PYVR_PERSISTENT 0   // 1: one wave of CTAs, warps pull tiles off an atomic queue (not with image-space sharding)
 #endif
 #ifndef PYVR_LANE_ARR
-#define PYVR_LANE_ARR 1     // measured on C3 (profiles/r02_lane_ab.txt): 4x2 blocks 477, 2x4 blocks 448-470, rows 449 Gsamples/s
+#define PYVR_LANE_ARR 4     // measured on C3 over the WHOLE turntable (profiles/r02_turntable_ab.txt), each with its best pitch
+                            // residues: rows (0) 447, 4x2 quarter blocks (1) 459, 2x2 pass blocks (3 / 4) 471 / 473 Gsamples/s
 #endif
 #ifndef PYVR_DENSITY_FIRST
 #define PYVR_DENSITY_FIRST 0   // measured (profiles/r02_density_first_ab.txt): 452 vs 482 Gsamples/s with ESS, 122 vs 130 dense
@@ -378,9 +379,11 @@ march_kernel(const __grid_constant__ MarchArgs a) {
     static_assert(!(TWO || TWO_B8) || (HALF && !STRICT && !TEX), "multi-sample march: f16x4 fast path only");
     constexpr int TEXEL_BYTES = HALF ? 8 : 16, ENTRY_BYTES = TEXEL_BYTES << (PAIR ? 1 : 0);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // lane -> pixel inside the warp's 8x4 tile.  The L1 data stage serves a warp-wide load quarter-warp by
-    // quarter-warp (lanes 8q .. 8q+7); how many distinct entries those 8 lanes touch, and on which banks, decides
-    // how many cycles a pass takes (tools/bank_sim.py, profiles/r02_lane_ab.txt).
+    // lane -> pixel inside the warp's 8x4 tile.  The L1 data stage serves a warp-wide LDG.256 in passes of four
+    // consecutive lanes (tools/l1_gather_probe.cu); how many distinct entries those lanes touch, and in which slots of
+    // their lines, decides how many cycles a pass takes (tools/bank_sim.py): a 2x2 pixel block per pass conflicts
+    // least.  The first A/Bs of round 2 marched views 0..15 only and preferred 4x1 passes (profiles/r02_lane_ab.txt);
+    // over all 360 views the 2x2 blocks win by 3 %.
 #if PYVR_LANE_ARR == 1      // quarter-warp = 4x2 pixel block
     const int lane_x = (lane & 3) + 4 * ((lane >> 3) & 1), lane_y = ((lane >> 2) & 1) + 2 * (lane >> 4);
 #elif PYVR_LANE_ARR == 2    // quarter-warp = 2x4 pixel block
