@@ -430,14 +430,15 @@ def time_normals(torch, _cabi, data, device, peak):
     }
 
 
-def active_texel_bytes(data, lut, entry_bytes):
-    """Bytes of packed texels in ACTIVE macrocells (8^3 voxels whose scalar range can reach a non-zero LUT alpha):
-    what the ESS march can touch per frame (SURVEY.md section 8 d, 'unique brick bytes touched')."""
+def active_texel_bytes(data, lut, entry_bytes, cell=4):
+    """Bytes of packed texels in ACTIVE macrocells (`cell`^3 voxels whose scalar range can reach a non-zero LUT alpha;
+    4 = the library's PYVR_CELL_SHIFT 2): what the ESS march can touch per frame (SURVEY.md section 8 d, 'unique brick
+    bytes touched')."""
     n = data.shape[0]
-    c = n // 8
-    if n % 8 or data.shape != (n, n, n):
+    c = n // cell
+    if n % cell or data.shape != (n, n, n):
         return None
-    hi = data.reshape(c, 8, c, 8, c, 8).max(axis=(1, 3, 5))
+    hi = data.reshape(c, cell, c, cell, c, cell).max(axis=(1, 3, 5))
     for axis in range(3):                                  # +1 apron the upper taps reach
         nb = np.concatenate([np.take(hi, range(1, c), axis=axis), np.take(hi, [c - 1], axis=axis)], axis=axis)
         hi = np.maximum(hi, nb)
@@ -445,7 +446,7 @@ def active_texel_bytes(data, lut, entry_bytes):
     nz = np.concatenate([[0], np.cumsum(lut[:, 3] != 0)])
     jh = np.clip(np.floor(hi.astype(np.float64) * size - 0.5) + 1, 0, size - 1).astype(np.int64)
     active = nz[jh + 1] > 0                                # lower end of every cell of this volume is ~0
-    return int(active.sum()) * 512 * entry_bytes, float(active.mean())
+    return int(active.sum()) * cell ** 3 * entry_bytes, float(active.mean())
 
 
 def traffic_per_view(args):
@@ -515,6 +516,7 @@ def main():
         renderer = VolumeRenderer(args.width, args.height, config=config, light=light, **renderer_kw)
         normals_info = {"device_generation_ms": renderer.generate_volume(args.size, "double_sphere", (-1, -1, -1), (1, 1, 1))}
     renderer.set_lut(lut)
+    texel_layout = renderer.texel_layout
     stream = torch.cuda.Stream()   # non-default: the library treats stream 0 as "use the context's own stream"
     renderer.set_stream(stream.cuda_stream)
     setup_s = time.perf_counter() - t_setup
@@ -638,14 +640,16 @@ def main():
         frames_per_s_kernel = views_per_launch / (launch_ms * 1e-3)
         hbm = None
         if data is not None:
-            got = active_texel_bytes(data, lut, 32 if args.texels == "f32" else 16)
+            texel_b = 16 if args.texels == "f32" else 8
+            entry_b = texel_b * (2 if "z-pair" in texel_layout else 1)
+            got = active_texel_bytes(data, lut, entry_b)
             if got is not None:
-                unique = got[0] if not args.no_ess else data.size * (32 if args.texels == "f32" else 16)
+                unique = got[0] if not args.no_ess else data.size * entry_b
                 hbm_achieved = (unique + frame_bytes) * frames_per_s_kernel / 1e9
                 hbm = {"achieved": hbm_achieved, "peak": peak, "unit": "GB/s", "frac": hbm_achieved / peak,
                        "unique_texel_bytes_per_frame": unique, "active_cell_fraction": got[1], "peak_source": peak_src,
                        "note": "SURVEY.md section 8(d): (unique brick bytes touched per frame + W*H*4) x frames/s of the kernel / "
-                               "HBM copy rate; unique = packed z-pair entries (32 B per voxel) of the active 8^3 macrocells"}
+                               f"HBM copy rate; unique = packed entries ({entry_b} B per voxel, layout: {texel_layout}) of the active 4^3 macrocells"}
         line = {
             "metric": "ray-march throughput", "value": value, "unit": "Gsamples/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
@@ -668,7 +672,7 @@ def main():
                 "peak_source": "measured live: pyvr_cuda_measure_cache_bandwidth(level 1) -- coalesced LDG.128 hitting L1, "
                                "bytes delivered to registers / CUDA-event time (csrc/bandwidth.cu)",
                 "peak_nominal": l1_nominal, "frac_of_nominal": achieved / l1_nominal,
-                "kernel": "march_kernel<fast, f32x4 z-pair>", "kernel_ms_per_launch": launch_ms, "views_per_launch": views_per_launch,
+                "kernel": f"march_kernel<fast, {args.texels}x4, {texel_layout}>", "kernel_ms_per_launch": launch_ms, "views_per_launch": views_per_launch,
                 "algorithmic_bytes_per_sample": bytes_per_sample,
                 "samples_fetched_per_launch": fetched_per_launch,
                 "samples_reference_per_launch": samples / max(launches, 1),

@@ -196,8 +196,12 @@ void choose_layout(pyvr_ctx *c, const int local[3], const int global[3]) {
     const size_t doubled = (size_t)local[0] * local[1] * local[2] * (c->half_texels ? 8 : 16) * 2;
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) free_b = 0;   // called after the old volume was freed
+    // z-pairs by default for f16x4 only.  For f32x4 they won every A/B on views 0..15 (profiles/r02_layout_ab.txt: 428
+    // vs 396 Gsamples/s with 4x1-pixel passes) but over the whole turntable, with the shipped 2x2-pixel passes, eight
+    // LDG.128 over eight 16-byte slots beat four LDG.256 over four 32-byte slots (profiles/r02_turntable_ab.txt: 486 vs
+    // 473) -- and need half the memory.
     c->use_pair = !c->use_brick8 &&
-                  (c->pair_option < 0 ? (double)doubled <= kPairBudget * (double)free_b : c->pair_option != 0);
+                  (c->pair_option < 0 ? (c->half_texels && (double)doubled <= kPairBudget * (double)free_b) : c->pair_option != 0);
 }
 
 // local[3] = stored texel counts along world x, y, z; global/org/own_* = NULL for a whole volume.

@@ -153,10 +153,11 @@ cudaError_t launch_pack_texels(const float *scalar, const float *normals, const 
 cudaError_t launch_fill_apron(const VolumeDesc &vol, bool half_texels, cudaStream_t stream);
 cudaError_t launch_cell_minmax(const VolumeDesc &vol, bool half_texels, float2 *cell_minmax,
                                cudaStream_t stream);
-// Macrocell edge of the empty-space map: 2^PYVR_CELL_SHIFT voxels.  8 measured against 4 on C3 in round 2
-// (profiles/r02_cell_ab.txt): smaller cells skip ~9 % more samples but the map walk visits more of them.
+// Macrocell edge of the empty-space map: 2^PYVR_CELL_SHIFT voxels.  Smaller cells skip ~9 % more samples of C3 but
+// the map walk visits more of them: 4^3 against 8^3 was a tie on views 0..15 and is +2 % over the whole turntable
+// (profiles/r02_turntable_ab.txt: 481 vs 473 with z-pairs, 495 vs 486 without).
 #ifndef PYVR_CELL_SHIFT
-#define PYVR_CELL_SHIFT 3
+#define PYVR_CELL_SHIFT 2
 #endif
 constexpr int kCellShift = PYVR_CELL_SHIFT, kCell = 1 << kCellShift;
 constexpr int kCellDistCap = 15;      // distances saturate here (a nibble); a saturated value is a lower bound
