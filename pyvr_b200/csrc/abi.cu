@@ -8,7 +8,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
 #include <new>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -469,6 +471,130 @@ int finish_stats(pyvr_ctx *c, size_t pairs, int views, bool defer = false) {
 }
 
 bool renderable(const pyvr_ctx *c) { return c->have_volume && c->lut_size > 0; }
+
+
+// ---- host-array path of compute_normal_volume: slabs of axis 0 through pinned staging, pipelined -----------------
+// The kernel needs 0.5 ms for 512^3; the host call is all copying (0.5 GiB in, 1.5 GiB out).  cudaMemcpy from / to
+// pageable numpy memory moved that at ~6 GB/s (0.38 s).  Here the volume travels in slabs of kSlabPlanes planes (+ one
+// halo plane on every cut side: interior planes then see their true neighbours, the kernel's one-sided differences only
+// ever apply to the volume's own faces, and the halo planes' results are dropped -- the same split as
+// multi_gpu.compute_normal_volume_sharded, bit-identical to the whole-volume call): host threads copy slab c+1 into
+// pinned memory and slab c-1 out of it while slab c is on the device (H2D + kernel on one stream, D2H on another).
+// The staging buffers are kept for the life of the process (pinned allocations cost ~0.3 ms per MiB).
+struct NormalsStaging {
+    int device = -1;
+    size_t in_bytes = 0, out_bytes = 0;
+    float *pin_in[2] = {nullptr, nullptr}, *pin_out[2] = {nullptr, nullptr}, *d_in[2] = {nullptr, nullptr}, *d_out[2] = {nullptr, nullptr};
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t h2d_done[2] = {nullptr, nullptr}, kernel_done[2] = {nullptr, nullptr}, d2h_done[2] = {nullptr, nullptr};
+};
+NormalsStaging g_normals_staging;
+std::mutex g_normals_staging_mutex;      // one host-array call at a time uses the staging buffers
+
+void parallel_copy(void *dst, const void *src, size_t bytes) {
+    constexpr size_t kMinPerThread = (size_t)4 << 20;
+    unsigned hw = std::thread::hardware_concurrency();
+    size_t n = bytes / kMinPerThread;
+    if (n > 8) n = 8;
+    if (hw && n > hw) n = hw;
+    if (n < 2) { memcpy(dst, src, bytes); return; }
+    std::vector<std::thread> pool;
+    const size_t part = ((bytes / n) + 63) & ~(size_t)63;
+    for (size_t i = 1; i < n; ++i) {
+        const size_t off = i * part, len = off >= bytes ? 0 : (i == n - 1 ? bytes - off : part);
+        if (len) pool.emplace_back([=] { memcpy(static_cast<char *>(dst) + off, static_cast<const char *>(src) + off, len); });
+    }
+    memcpy(dst, src, part < bytes ? part : bytes);
+    for (auto &t : pool) t.join();
+}
+
+cudaError_t ensure_normals_staging(NormalsStaging &st, int device, size_t in_bytes, size_t out_bytes) {
+    cudaError_t e = cudaSuccess;
+    if (st.device != device || st.in_bytes < in_bytes || st.out_bytes < out_bytes) {
+        for (int i = 0; i < 2; ++i) {
+            if (st.pin_in[i]) cudaFreeHost(st.pin_in[i]);
+            if (st.pin_out[i]) cudaFreeHost(st.pin_out[i]);
+            if (st.d_in[i]) cudaFree(st.d_in[i]);
+            if (st.d_out[i]) cudaFree(st.d_out[i]);
+            st.pin_in[i] = st.pin_out[i] = st.d_in[i] = st.d_out[i] = nullptr;
+        }
+        st.in_bytes = st.out_bytes = 0;
+        for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+            e = cudaMallocHost(&st.pin_in[i], in_bytes);
+            if (e == cudaSuccess) e = cudaMallocHost(&st.pin_out[i], out_bytes);
+            if (e == cudaSuccess) e = cudaMalloc(&st.d_in[i], in_bytes);
+            if (e == cudaSuccess) e = cudaMalloc(&st.d_out[i], out_bytes);
+        }
+        if (e != cudaSuccess) return e;
+        st.in_bytes = in_bytes; st.out_bytes = out_bytes; st.device = device;
+    }
+    if (!st.s_in) {
+        e = cudaStreamCreateWithFlags(&st.s_in, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&st.s_out, cudaStreamNonBlocking);
+        for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+            e = cudaEventCreateWithFlags(&st.h2d_done[i], cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventCreate(&st.kernel_done[i]);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&st.d2h_done[i], cudaEventDisableTiming);
+        }
+    }
+    return e;
+}
+
+constexpr int kSlabPlanes = 16;
+
+// in / out: host arrays.  kernel_ms (may be NULL): sum of the slab kernels' device times.
+cudaError_t normals_host_pipeline(int device, const float *in, float *out, int n0, int n1, int n2, bool relaxed, float *kernel_ms) {
+    std::lock_guard<std::mutex> lock(g_normals_staging_mutex);
+    NormalsStaging &st = g_normals_staging;
+    const size_t plane = (size_t)n1 * n2;
+    const int slab = n0 < kSlabPlanes ? n0 : kSlabPlanes;
+    cudaError_t e = ensure_normals_staging(st, device, (size_t)(slab + 2) * plane * sizeof(float), (size_t)(slab + 2) * plane * 3 * sizeof(float));
+    if (e != cudaSuccess) return e;
+    const int n_slabs = (n0 + slab - 1) / slab;
+    std::vector<cudaEvent_t> k0(n_slabs, nullptr);
+    float total_ms = 0.0f;
+    struct Pending { int p0, planes, slot; bool valid; } prev{0, 0, 0, false};
+    auto drain = [&](const Pending &q) -> cudaError_t {      // slab q: device -> pinned is done, pinned -> caller's array
+        cudaError_t d = cudaEventSynchronize(st.d2h_done[q.slot]);
+        if (d != cudaSuccess) return d;
+        parallel_copy(out + (size_t)q.p0 * plane * 3, st.pin_out[q.slot], (size_t)q.planes * plane * 3 * sizeof(float));
+        float ms = 0.0f;
+        d = cudaEventElapsedTime(&ms, k0[q.p0 / slab], st.kernel_done[q.slot]);
+        total_ms += ms;
+        return d;
+    };
+    for (int c = 0; c < n_slabs && e == cudaSuccess; ++c) {
+        const int slot = c & 1, p0 = c * slab, planes = n0 - p0 < slab ? n0 - p0 : slab;
+        const int lo = p0 > 0 ? 1 : 0, hi = p0 + planes < n0 ? 1 : 0, planes_in = planes + lo + hi;
+        // pinned_in[slot] / d_in[slot] are free once the H2D copy / the kernel of slab c-2 are done; both are ordered on
+        // s_in, and the host only has to wait for the copy before it overwrites the pinned buffer
+        if (c >= 2) e = cudaEventSynchronize(st.h2d_done[slot]);
+        if (e != cudaSuccess) break;
+        parallel_copy(st.pin_in[slot], in + (size_t)(p0 - lo) * plane, (size_t)planes_in * plane * sizeof(float));
+        e = cudaMemcpyAsync(st.d_in[slot], st.pin_in[slot], (size_t)planes_in * plane * sizeof(float), cudaMemcpyHostToDevice, st.s_in);
+        if (e == cudaSuccess) e = cudaEventRecord(st.h2d_done[slot], st.s_in);
+        // d_out[slot] is free once the D2H copy of slab c-2 has read it
+        if (e == cudaSuccess && c >= 2) e = cudaStreamWaitEvent(st.s_in, st.d2h_done[slot], 0);
+        if (e == cudaSuccess) e = cudaEventCreate(&k0[c]);
+        if (e == cudaSuccess) e = cudaEventRecord(k0[c], st.s_in);
+        if (e == cudaSuccess) e = launch_normals(st.d_in[slot], st.d_out[slot], planes_in, n1, n2, relaxed, st.s_in);
+        if (e == cudaSuccess) e = cudaEventRecord(st.kernel_done[slot], st.s_in);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(st.s_out, st.kernel_done[slot], 0);
+        // pinned_out[slot] was drained (slab c-2) in the previous iteration
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(st.pin_out[slot], st.d_out[slot] + (size_t)lo * plane * 3, (size_t)planes * plane * 3 * sizeof(float),
+                                cudaMemcpyDeviceToHost, st.s_out);
+        if (e == cudaSuccess) e = cudaEventRecord(st.d2h_done[slot], st.s_out);
+        if (e == cudaSuccess && prev.valid) e = drain(prev);
+        prev = Pending{p0, planes, slot, true};
+    }
+    if (e == cudaSuccess && prev.valid) e = drain(prev);
+    cudaStreamSynchronize(st.s_in);
+    cudaStreamSynchronize(st.s_out);
+    for (cudaEvent_t ev : k0) if (ev) cudaEventDestroy(ev);
+    if (e == cudaSuccess && kernel_ms) *kernel_ms = total_ms;
+    return e;
+}
 
 }  // namespace
 
@@ -1046,6 +1172,12 @@ int pyvr_cuda_compute_normals(int device, const float *in, float *out, int n0, i
     if (device < 0 || device >= n_dev) return fail(PYVR_ERR_INVALID, "device %d out of range (%d visible)", device, n_dev);
     DeviceGuard guard(device);
     const size_t voxels = (size_t)n0 * n1 * n2;
+    // host arrays of some size: slabs through pinned staging (PYVR_NORMALS_HOST_PIPELINE=0: the plain staged copy below)
+    static const bool pipeline = !(getenv("PYVR_NORMALS_HOST_PIPELINE") && atoi(getenv("PYVR_NORMALS_HOST_PIPELINE")) == 0);
+    if (!buffers_are_device && pipeline && voxels >= ((size_t)1 << 22) && (size_t)n1 * n2 * (kSlabPlanes + 2) * 16 <= ((size_t)1 << 31)) {
+        CU(normals_host_pipeline(device, in, out, n0, n1, n2, relaxed, kernel_ms));
+        return PYVR_OK;
+    }
     const float *d_in = in;
     float *d_out = out, *stage_in = nullptr, *stage_out = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;

@@ -98,6 +98,19 @@ def test_large_volume_vs_oracle_and_timing():
     assert 0 < ms < 50
 
 
+@pytest.mark.parametrize("shape", [(37, 300, 384), (70, 250, 251), (16, 512, 512), (17, 512, 512), (1, 2048, 2048)])
+def test_host_pipeline_slabs_are_bit_exact(shape):
+    """Host arrays of >= 4 M voxels travel in 16-plane slabs (+ halo planes) through pinned staging
+    (abi.cu, normals_host_pipeline): every plane must come out as in the whole-volume call -- slab counts that do
+    and do not divide the volume, a ragged fastest axis (scalar kernel), a single plane."""
+    rng = np.random.default_rng(sum(shape))
+    vol = rng.random(shape, dtype=np.float32)
+    vol[:, :7, :9] = 0.0
+    got, ms = _cabi.compute_normals_host(vol, return_ms=True)
+    _check(got, oracle.normals(vol), f"pipeline {shape}")
+    assert ms > 0
+
+
 def test_volume_compute_normals_method_and_dtype_cast():
     v = Volume(data=create_sample_volume(24, "torus").astype(np.float64))
     v.compute_normals()
