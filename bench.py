@@ -69,7 +69,7 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--no-alternatives", action="store_true", help="skip the f16 / hwtex / dense side measurements")
-    ap.add_argument("--no-secondary", action="store_true", help="N > 1: skip the C4 / C5 lines and the parity check")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the C4 (N = 1) / C4 + C5 + parity check (N > 1) section")
     ap.add_argument("--secondary-seconds", type=float, default=240.0, help="N > 1: time box of the secondary section")
     ap.add_argument("--reference-backend", default="auto", choices=["auto", "gl", "oracle"],
                     help="CPU arm: gl = the reference's GLSL on Mesa llvmpipe; oracle = C/OpenMP restatement")
@@ -709,7 +709,21 @@ def main():
         secondary = bench_partitioned.secondary_section(args, rank, world, local_rank, line, args.secondary_seconds)
         if rank == 0:
             line.update(secondary)
-    elif rank == 0 and not args.skip_cpu_baseline and world == 1:
+    if world == 1 and rank == 0 and not args.no_secondary:
+        # N = 1: config C4 (2048^3 f16 scalar+normal, 3840x2160, ultra preset) as ONE frame stream on this GPU, so that the
+        # single-GPU number behind the N > 1 tile lines is in the driver's own BENCH line too.  ~15 s, 65 GiB on the device;
+        # nothing here may cost the main line.
+        try:
+            import bench_partitioned
+
+            c4 = bench_partitioned.measure(args, 0, 1, local_rank, "c4", steps=8, warmup=2)
+            keep = ("value", "unit", "ms_per_step", "frames_per_s", "samples_per_frame", "config", "e2e", "roofline", "clocks",
+                    "volume_generation", "steps", "warmup", "n_gpus")
+            line["secondary"] = {"c4": {k: c4[k] for k in keep if k in c4}}
+        except Exception as e:
+            line["secondary"] = {"c4": {"error": f"{type(e).__name__}: {e}"}}
+        torch.cuda.empty_cache()
+    if rank == 0 and not args.skip_cpu_baseline and world == 1:
         cores = use_all_host_threads()
         try:
             ref = CpuReference(args, data, normals, light, config, lut, args.reference_backend)
